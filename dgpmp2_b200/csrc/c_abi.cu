@@ -1,0 +1,427 @@
+// extern "C" entry points of libdgpmp2_b200.so (declared in include/dgpmp2_b200.h).
+// Host-side argument checking, derived constants, launch-shape selection, launches.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/dgpmp2_b200.h"
+#include "kernels.cuh"
+
+using namespace dgpmp2;
+
+namespace {
+
+thread_local char g_cuda_err[256] = {0};
+
+int cuda_fail(cudaError_t e) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+  return DGPMP2_ERR_CUDA;
+}
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_); } while (0)
+
+constexpr int kSmemLimit = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
+
+int check_params(const dgpmp2_params* p, const dgpmp2_weights* w) {
+  if (p == nullptr) return DGPMP2_ERR_ARG;
+  if (p->B < 0 || p->T < 2 || p->H < 1 || p->W < 1) return DGPMP2_ERR_ARG;
+  if (p->dof != 2 && p->dof != 3) return DGPMP2_ERR_UNSUPPORTED;
+  if (p->flags & ~(DGPMP2_FLAG_NONHOLONOMIC | DGPMP2_FLAG_VEL_LIMITS | DGPMP2_FLAG_Q_FULL)) return DGPMP2_ERR_ARG;
+  if ((p->flags & DGPMP2_FLAG_NONHOLONOMIC) && (p->flags & DGPMP2_FLAG_VEL_LIMITS)) return DGPMP2_ERR_ARG;
+  if ((p->flags & DGPMP2_FLAG_NONHOLONOMIC) && p->dof != 3) return DGPMP2_ERR_ARG;
+  if ((p->flags & DGPMP2_FLAG_VEL_LIMITS) && p->dof != 2) return DGPMP2_ERR_ARG;
+  if ((p->flags & DGPMP2_FLAG_Q_FULL) && (w == nullptr || w->qc_inv == nullptr)) return DGPMP2_ERR_ARG;
+  if (!(p->res > 0.0) || !(p->dt > 0.0)) return DGPMP2_ERR_ARG;
+  if (p->sdf_stride_b < 0) return DGPMP2_ERR_ARG;
+  return DGPMP2_OK;
+}
+
+KParams make_kparams(const dgpmp2_params* p) {
+  KParams k;
+  memset(&k, 0, sizeof(k));
+  k.B = p->B; k.T = p->T; k.H = p->H; k.W = p->W; k.flags = p->flags;
+  const int d = 2 * p->dof;
+  // plan_layer.py:39-45
+  k.M = d * ((p->T - 1) + 2) + p->T;
+  if (p->flags & DGPMP2_FLAG_NONHOLONOMIC) k.M += p->T;
+  if (p->flags & DGPMP2_FLAG_VEL_LIMITS) k.M += p->dof * p->T;
+  k.sdf_sb = p->sdf_stride_b;
+  k.res = p->res;
+  k.orig_x = 0.0 - p->x_lo / p->res;          // sdf_utils.py:57
+  k.orig_y = 0.0 - p->y_lo / p->res;          // sdf_utils.py:58
+  k.dt = p->dt;
+  k.qa = 12.0 * std::pow(p->dt, -3.0);        // gp_factor.py:66-68
+  k.qb = -6.0 * std::pow(p->dt, -2.0);
+  k.qc = 4.0 * std::pow(p->dt, -1.0);
+  k.r_sphere = p->r_sphere; k.ks = p->ks_inv2; k.kg = p->kg_inv2; k.reg = p->reg;
+  k.kd = p->kd_inv2; k.kv = p->kv_inv2; k.vx_lim = p->vx_lim; k.vy_lim = p->vy_lim;
+  for (int i = 0; i < 9; ++i) { k.qc_const[i] = p->qc_inv[i]; k.qc_fix[i] = p->qc_inv_fix[i]; }
+  k.w_const = p->w_obs; k.w_fix = p->w_obs_fix; k.eps_const = p->eps;
+  return k;
+}
+
+template <typename IO>
+KWeights<IO> make_kweights(const dgpmp2_weights* w) {
+  KWeights<IO> k;
+  memset(&k, 0, sizeof(k));
+  if (w != nullptr) {
+    k.qc = static_cast<const IO*>(w->qc_inv); k.qc_sb = w->qc_stride_b; k.qc_st = w->qc_stride_t;
+    k.w = static_cast<const IO*>(w->w_obs); k.w_sb = w->w_stride_b; k.w_st = w->w_stride_t;
+    k.eps = static_cast<const IO*>(w->eps); k.e_sb = w->eps_stride_b; k.e_st = w->eps_stride_t;
+  }
+  return k;
+}
+
+struct LaunchShape { int np, threads, smem, grid; };
+
+// Problems per CTA: aim for ~256 threads (one per trajectory state) and <= half an SM's shared
+// memory so that two CTAs are co-resident and one CTA's sparse BCR levels overlap the other's
+// dense ones.  DGPMP2_NP overrides (tuning only).
+template <int D, typename IO>
+int choose_shape(int B, int T, bool solve, LaunchShape& s) {
+  const int max_threads = (D == 4) ? 512 : 256;
+  int np = 256 / T;
+  if (np < 1) np = 1;
+  if (const char* e = getenv("DGPMP2_NP")) { const int v = atoi(e); if (v > 0) np = v; }
+  if (np > B) np = B;
+  if (np < 1) np = 1;
+  const size_t half = kSmemLimit / 2 - 1024;
+  while (np > 1 && StepSmem<D, IO>::bytes(np, T, solve) > half) --np;
+  if (getenv("DGPMP2_NP")) {   // explicit override may use the whole SM
+    np = atoi(getenv("DGPMP2_NP"));
+    if (np > B) np = B;
+    if (np < 1) np = 1;
+    while (np > 1 && StepSmem<D, IO>::bytes(np, T, solve) > (size_t)kSmemLimit) --np;
+  }
+  const size_t bytes = StepSmem<D, IO>::bytes(np, T, solve);
+  if (bytes > (size_t)kSmemLimit) return DGPMP2_ERR_UNSUPPORTED;
+  int threads = ((np * T + 31) / 32) * 32;
+  if (threads > max_threads) threads = max_threads;
+  if (const char* e = getenv("DGPMP2_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= max_threads) threads = (v / 32) * 32; }
+  s.np = np; s.threads = threads; s.smem = (int)bytes; s.grid = (B + np - 1) / np;
+  return DGPMP2_OK;
+}
+
+template <typename K>
+int allow_smem(K kernel, int bytes) {
+  if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  return DGPMP2_OK;
+}
+
+template <int DOF, typename IO>
+int launch_step(const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start, const IO* goal, const IO* sdf,
+                IO* dth, IO* err, IO* err_ext, int32_t* status, cudaStream_t st) {
+  LaunchShape s;
+  int rc = choose_shape<2 * DOF, IO>(k.B, k.T, false, s);
+  if (rc != DGPMP2_OK) return rc;
+  auto kern = gn_step_kernel<DOF, IO>;
+  rc = allow_smem(kern, s.smem);
+  if (rc != DGPMP2_OK) return rc;
+  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, s.np);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
+}
+
+template <typename IO>
+int gn_step_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO* goal, const IO* sdf,
+                 const dgpmp2_weights* w, IO* dth, IO* err, IO* err_ext, int32_t* status, void* stream) {
+  int rc = check_params(p, w);
+  if (rc != DGPMP2_OK) return rc;
+  if (p->B == 0) return DGPMP2_OK;
+  if (!th || !start || !goal || !sdf || !dth || !err || !err_ext) return DGPMP2_ERR_ARG;
+  const KParams k = make_kparams(p);
+  const KWeights<IO> kw = make_kweights<IO>(w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dof == 2) return launch_step<2, IO>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
+  return launch_step<3, IO>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
+}
+
+template <int DOF, typename IO>
+int launch_solve(const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start, const IO* goal, const IO* sdf,
+                 int max_iters, double tol, IO* th_final, int32_t* iters, IO* epi, IO* eepi, IO* ef, IO* eef,
+                 int32_t* status, cudaStream_t st) {
+  LaunchShape s;
+  int rc = choose_shape<2 * DOF, IO>(k.B, k.T, true, s);
+  if (rc != DGPMP2_OK) return rc;
+  auto kern = gn_solve_kernel<DOF, IO>;
+  rc = allow_smem(kern, s.smem);
+  if (rc != DGPMP2_OK) return rc;
+  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, max_iters, tol, th_final, iters, epi, eepi, ef,
+                                          eef, status, s.np);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
+}
+
+template <typename IO>
+int gn_solve_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO* goal, const IO* sdf,
+                  const dgpmp2_weights* w, int32_t max_iters, double tol, IO* th_final, int32_t* iters, IO* epi,
+                  IO* eepi, IO* ef, IO* eef, int32_t* status, void* stream) {
+  int rc = check_params(p, w);
+  if (rc != DGPMP2_OK) return rc;
+  if (max_iters < 1) return DGPMP2_ERR_ARG;
+  if (p->B == 0) return DGPMP2_OK;
+  if (!th || !start || !goal || !sdf || !th_final || !iters) return DGPMP2_ERR_ARG;
+  const KParams k = make_kparams(p);
+  const KWeights<IO> kw = make_kweights<IO>(w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dof == 2)
+    return launch_solve<2, IO>(k, kw, th, start, goal, sdf, max_iters, tol, th_final, iters, epi, eepi, ef, eef, status, st);
+  return launch_solve<3, IO>(k, kw, th, start, goal, sdf, max_iters, tol, th_final, iters, epi, eepi, ef, eef, status, st);
+}
+
+template <typename IO>
+int errors_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO* goal, const IO* sdf,
+                const dgpmp2_weights* w, IO* err, IO* err_ext, IO* err_sg, IO* err_gp, IO* err_obs, void* stream) {
+  int rc = check_params(p, w);
+  if (rc != DGPMP2_OK) return rc;
+  if (p->B == 0) return DGPMP2_OK;
+  if (!th || !start || !goal || !sdf) return DGPMP2_ERR_ARG;
+  const KParams k = make_kparams(p);
+  const KWeights<IO> kw = make_kweights<IO>(w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int threads = ((p->T + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (p->dof == 2)
+    errors_kernel<2, IO><<<p->B, threads, 0, st>>>(k, kw, th, start, goal, sdf, err, err_ext, err_sg, err_gp, err_obs);
+  else
+    errors_kernel<3, IO><<<p->B, threads, 0, st>>>(k, kw, th, start, goal, sdf, err, err_ext, err_sg, err_gp, err_obs);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
+}
+
+int grid_for(long long n, int threads) {
+  long long g = (n + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <typename IO>
+int factors_impl(const dgpmp2_params* p, const IO* th, const IO* sdf, const dgpmp2_weights* w, IO* gp_err,
+                 IO* obs_cost, IO* obs_H, IO* cust_err, IO* cust_H, void* stream) {
+  dgpmp2_params q = *p;
+  q.flags &= ~DGPMP2_FLAG_Q_FULL;   // GP covariance is not read here
+  int rc = check_params(&q, w);
+  if (rc != DGPMP2_OK) return rc;
+  if (p->B == 0) return DGPMP2_OK;
+  if (!th) return DGPMP2_ERR_ARG;
+  if ((obs_cost || obs_H) && !sdf) return DGPMP2_ERR_ARG;
+  const KParams k = make_kparams(&q);
+  const KWeights<IO> kw = make_kweights<IO>(w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int g = grid_for((long long)p->B * p->T, 256);
+  if (p->dof == 2)
+    factors_kernel<2, IO><<<g, 256, 0, st>>>(k, kw, th, sdf, gp_err, obs_cost, obs_H, cust_err, cust_H);
+  else
+    factors_kernel<3, IO><<<g, 256, 0, st>>>(k, kw, th, sdf, gp_err, obs_cost, obs_H, cust_err, cust_H);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
+}
+
+template <typename IO>
+int band_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO* goal, const IO* sdf,
+              const dgpmp2_weights* w, double* D, double* U, double* r, void* stream) {
+  int rc = check_params(p, w);
+  if (rc != DGPMP2_OK) return rc;
+  if (p->B == 0) return DGPMP2_OK;
+  if (!th || !start || !goal || !sdf || !D || !U || !r) return DGPMP2_ERR_ARG;
+  const KParams k = make_kparams(p);
+  const KWeights<IO> kw = make_kweights<IO>(w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int g = grid_for((long long)p->B * p->T, 128);
+  if (p->dof == 2) band_kernel<2, IO><<<g, 128, 0, st>>>(k, kw, th, start, goal, sdf, D, U, r);
+  else band_kernel<3, IO><<<g, 128, 0, st>>>(k, kw, th, start, goal, sdf, D, U, r);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
+}
+
+template <typename IO>
+int sdf_lookup_impl(const IO* sdf, int32_t B, int32_t H, int32_t W, int64_t sdf_sb, const IO* pts, int32_t N,
+                    double res, double x_lo, double y_lo, IO* dist, IO* J, void* stream) {
+  if (B < 0 || N < 0 || H < 1 || W < 1 || !(res > 0.0) || sdf_sb < 0) return DGPMP2_ERR_ARG;
+  if (B == 0 || N == 0) return DGPMP2_OK;
+  if (!sdf || !pts) return DGPMP2_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const double ox = 0.0 - x_lo / res, oy = 0.0 - y_lo / res;
+  sdf_lookup_kernel<IO><<<grid_for((long long)B * N, 256), 256, 0, st>>>(sdf, B, H, W, sdf_sb, pts, N, res, ox, oy, dist, J);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct HostWs { size_t th, start, goal, sdf, dth, err, err_ext, status, total; };
+
+HostWs host_ws_layout(const dgpmp2_params* p, size_t es) {
+  const size_t B = p->B, T = p->T, d = 2 * p->dof;
+  const size_t sdf_elems = (p->sdf_stride_b == 0) ? (size_t)p->H * p->W : (size_t)p->sdf_stride_b * B;
+  HostWs w;
+  size_t o = 0;
+  w.th = o; o += align256(B * T * d * es);
+  w.start = o; o += align256(B * d * es);
+  w.goal = o; o += align256(B * d * es);
+  w.sdf = o; o += align256(sdf_elems * es);
+  w.dth = o; o += align256(B * T * d * es);
+  w.err = o; o += align256(B * es);
+  w.err_ext = o; o += align256(B * es);
+  w.status = o; o += align256(B * 4);
+  w.total = o;
+  return w;
+}
+
+template <typename IO>
+int gn_step_host_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO* goal, const IO* sdf, IO* dth,
+                      IO* err, IO* err_ext, int32_t* status, void* dev_ws, size_t dev_ws_bytes, int32_t sdf_resident,
+                      void* stream) {
+  int rc = check_params(p, nullptr);
+  if (rc != DGPMP2_OK) return rc;
+  if (p->B == 0) return DGPMP2_OK;
+  if (!th || !start || !goal || !dth || !err || !err_ext || !dev_ws) return DGPMP2_ERR_ARG;
+  if (!sdf_resident && !sdf) return DGPMP2_ERR_ARG;
+  const HostWs L = host_ws_layout(p, sizeof(IO));
+  if (dev_ws_bytes < L.total) return DGPMP2_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned char* ws = static_cast<unsigned char*>(dev_ws);
+  const size_t B = p->B, T = p->T, d = 2 * p->dof;
+  const size_t sdf_elems = (p->sdf_stride_b == 0) ? (size_t)p->H * p->W : (size_t)p->sdf_stride_b * B;
+  CUDA_TRY(cudaMemcpyAsync(ws + L.th, th, B * T * d * sizeof(IO), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ws + L.start, start, B * d * sizeof(IO), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ws + L.goal, goal, B * d * sizeof(IO), cudaMemcpyHostToDevice, st));
+  if (!sdf_resident) CUDA_TRY(cudaMemcpyAsync(ws + L.sdf, sdf, sdf_elems * sizeof(IO), cudaMemcpyHostToDevice, st));
+  rc = gn_step_impl<IO>(p, reinterpret_cast<IO*>(ws + L.th), reinterpret_cast<IO*>(ws + L.start),
+                        reinterpret_cast<IO*>(ws + L.goal), reinterpret_cast<IO*>(ws + L.sdf), nullptr,
+                        reinterpret_cast<IO*>(ws + L.dth), reinterpret_cast<IO*>(ws + L.err),
+                        reinterpret_cast<IO*>(ws + L.err_ext), reinterpret_cast<int32_t*>(ws + L.status), stream);
+  if (rc != DGPMP2_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(dth, ws + L.dth, B * T * d * sizeof(IO), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(err, ws + L.err, B * sizeof(IO), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(err_ext, ws + L.err_ext, B * sizeof(IO), cudaMemcpyDeviceToHost, st));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, ws + L.status, B * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return DGPMP2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dgpmp2_abi_version(void) { return DGPMP2_ABI_VERSION; }
+
+const char* dgpmp2_status_string(int code) {
+  switch (code) {
+    case DGPMP2_OK: return "ok";
+    case DGPMP2_ERR_ARG: return "invalid argument";
+    case DGPMP2_ERR_UNSUPPORTED: return "unsupported configuration (dof not in {2,3} or trajectory too long for on-chip band)";
+    case DGPMP2_ERR_CUDA: return "CUDA runtime error";
+    default: return "unknown status";
+  }
+}
+
+const char* dgpmp2_last_cuda_error(void) { return g_cuda_err; }
+
+int dgpmp2_gn_step_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal, const float* sdf,
+                       const dgpmp2_weights* w, float* dth, float* err, float* err_ext, int32_t* status, void* stream) {
+  return gn_step_impl<float>(p, th, start, goal, sdf, w, dth, err, err_ext, status, stream);
+}
+int dgpmp2_gn_step_f64(const dgpmp2_params* p, const double* th, const double* start, const double* goal,
+                       const double* sdf, const dgpmp2_weights* w, double* dth, double* err, double* err_ext,
+                       int32_t* status, void* stream) {
+  return gn_step_impl<double>(p, th, start, goal, sdf, w, dth, err, err_ext, status, stream);
+}
+
+int dgpmp2_gn_solve_f32(const dgpmp2_params* p, const float* th_init, const float* start, const float* goal,
+                        const float* sdf, const dgpmp2_weights* w, int32_t max_iters, double tol_delta, float* th_final,
+                        int32_t* iters, float* err_per_iter, float* err_ext_per_iter, float* err_final,
+                        float* err_ext_final, int32_t* status, void* stream) {
+  return gn_solve_impl<float>(p, th_init, start, goal, sdf, w, max_iters, tol_delta, th_final, iters, err_per_iter,
+                              err_ext_per_iter, err_final, err_ext_final, status, stream);
+}
+int dgpmp2_gn_solve_f64(const dgpmp2_params* p, const double* th_init, const double* start, const double* goal,
+                        const double* sdf, const dgpmp2_weights* w, int32_t max_iters, double tol_delta,
+                        double* th_final, int32_t* iters, double* err_per_iter, double* err_ext_per_iter,
+                        double* err_final, double* err_ext_final, int32_t* status, void* stream) {
+  return gn_solve_impl<double>(p, th_init, start, goal, sdf, w, max_iters, tol_delta, th_final, iters, err_per_iter,
+                               err_ext_per_iter, err_final, err_ext_final, status, stream);
+}
+
+int dgpmp2_errors_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal, const float* sdf,
+                      const dgpmp2_weights* w, float* err, float* err_ext, float* err_sg, float* err_gp, float* err_obs,
+                      void* stream) {
+  return errors_impl<float>(p, th, start, goal, sdf, w, err, err_ext, err_sg, err_gp, err_obs, stream);
+}
+int dgpmp2_errors_f64(const dgpmp2_params* p, const double* th, const double* start, const double* goal,
+                      const double* sdf, const dgpmp2_weights* w, double* err, double* err_ext, double* err_sg,
+                      double* err_gp, double* err_obs, void* stream) {
+  return errors_impl<double>(p, th, start, goal, sdf, w, err, err_ext, err_sg, err_gp, err_obs, stream);
+}
+
+int dgpmp2_factors_f32(const dgpmp2_params* p, const float* th, const float* sdf, const dgpmp2_weights* w, float* gp_err,
+                       float* obs_cost, float* obs_H, float* cust_err, float* cust_H, void* stream) {
+  if (p == nullptr) return DGPMP2_ERR_ARG;
+  return factors_impl<float>(p, th, sdf, w, gp_err, obs_cost, obs_H, cust_err, cust_H, stream);
+}
+int dgpmp2_factors_f64(const dgpmp2_params* p, const double* th, const double* sdf, const dgpmp2_weights* w,
+                       double* gp_err, double* obs_cost, double* obs_H, double* cust_err, double* cust_H, void* stream) {
+  if (p == nullptr) return DGPMP2_ERR_ARG;
+  return factors_impl<double>(p, th, sdf, w, gp_err, obs_cost, obs_H, cust_err, cust_H, stream);
+}
+
+int dgpmp2_sdf_lookup_f32(const float* sdf, int32_t B, int32_t H, int32_t W, int64_t sdf_stride_b, const float* pts,
+                          int32_t N, double res, double x_lo, double y_lo, float* dist, float* J, void* stream) {
+  return sdf_lookup_impl<float>(sdf, B, H, W, sdf_stride_b, pts, N, res, x_lo, y_lo, dist, J, stream);
+}
+int dgpmp2_sdf_lookup_f64(const double* sdf, int32_t B, int32_t H, int32_t W, int64_t sdf_stride_b, const double* pts,
+                          int32_t N, double res, double x_lo, double y_lo, double* dist, double* J, void* stream) {
+  return sdf_lookup_impl<double>(sdf, B, H, W, sdf_stride_b, pts, N, res, x_lo, y_lo, dist, J, stream);
+}
+
+int dgpmp2_band_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal, const float* sdf,
+                    const dgpmp2_weights* w, double* D, double* U, double* r, void* stream) {
+  return band_impl<float>(p, th, start, goal, sdf, w, D, U, r, stream);
+}
+int dgpmp2_band_f64(const dgpmp2_params* p, const double* th, const double* start, const double* goal,
+                    const double* sdf, const dgpmp2_weights* w, double* D, double* U, double* r, void* stream) {
+  return band_impl<double>(p, th, start, goal, sdf, w, D, U, r, stream);
+}
+
+int dgpmp2_host_step_workspace_bytes(const dgpmp2_params* p, int32_t elem_size, size_t* bytes) {
+  if (p == nullptr || bytes == nullptr || (elem_size != 4 && elem_size != 8)) return DGPMP2_ERR_ARG;
+  int rc = check_params(p, nullptr);
+  if (rc != DGPMP2_OK) return rc;
+  *bytes = host_ws_layout(p, (size_t)elem_size).total;
+  return DGPMP2_OK;
+}
+int dgpmp2_gn_step_host_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal,
+                            const float* sdf, float* dth, float* err, float* err_ext, int32_t* status, void* dev_ws,
+                            size_t dev_ws_bytes, int32_t sdf_resident, void* stream) {
+  return gn_step_host_impl<float>(p, th, start, goal, sdf, dth, err, err_ext, status, dev_ws, dev_ws_bytes,
+                                  sdf_resident, stream);
+}
+int dgpmp2_gn_step_host_f64(const dgpmp2_params* p, const double* th, const double* start, const double* goal,
+                            const double* sdf, double* dth, double* err, double* err_ext, int32_t* status, void* dev_ws,
+                            size_t dev_ws_bytes, int32_t sdf_resident, void* stream) {
+  return gn_step_host_impl<double>(p, th, start, goal, sdf, dth, err, err_ext, status, dev_ws, dev_ws_bytes,
+                                   sdf_resident, stream);
+}
+
+int dgpmp2_gn_step_launch_shape(const dgpmp2_params* p, int32_t elem_size, int32_t* problems_per_cta, int32_t* threads,
+                                int32_t* smem_bytes, int32_t* grid) {
+  if (p == nullptr || (elem_size != 4 && elem_size != 8)) return DGPMP2_ERR_ARG;
+  dgpmp2_params q = *p;
+  q.flags &= ~DGPMP2_FLAG_Q_FULL;
+  int rc = check_params(&q, nullptr);
+  if (rc != DGPMP2_OK) return rc;
+  LaunchShape s{0, 0, 0, 0};
+  const int B = p->B > 0 ? p->B : 1;
+  if (p->dof == 2) rc = (elem_size == 4) ? choose_shape<4, float>(B, p->T, false, s) : choose_shape<4, double>(B, p->T, false, s);
+  else rc = (elem_size == 4) ? choose_shape<6, float>(B, p->T, false, s) : choose_shape<6, double>(B, p->T, false, s);
+  if (rc != DGPMP2_OK) return rc;
+  if (problems_per_cta) *problems_per_cta = s.np;
+  if (threads) *threads = s.threads;
+  if (smem_bytes) *smem_bytes = s.smem;
+  if (grid) *grid = s.grid;
+  return DGPMP2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,337 @@
+// Per-state factor evaluation shared by every kernel of the GN path (sm_100a).
+//
+// One call of assemble_node() evaluates, for trajectory state t of one problem,
+// every factor that touches it -- start/goal prior, the two adjacent GP-prior
+// factors, the SDF obstacle factor (bilinear lookup + hinge + Jacobian) and the
+// optional nonholonomic / velocity-limit factor -- and returns that state's row
+// of the block-tridiagonal normal equations (D_t, U_t, r_t) together with its
+// contribution to the weighted and "external" errors.  The reference's dense
+// A, b, K (plan_layer.py:152-200) are never formed.
+//
+// All arithmetic is IEEE double.  Where the reference takes a data-dependent
+// branch (pixel floor, hinge test) the operation order of the reference is
+// reproduced so the branch sees bit-identical numbers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dgpmp2 {
+
+// Kernel-side constants (by-value kernel argument).
+struct KParams {
+  int B, T, H, W, flags, M;
+  long long sdf_sb;
+  double orig_x, orig_y, res;      // sdf_utils.py:57-58, obstacle_cost.py:34
+  double dt, qa, qb, qc;           // 12 dt^-3, -6 dt^-2, 4 dt^-1   (gp_factor.py:66-68)
+  double r_sphere, ks, kg, reg, kd, kv, vx_lim, vy_lim;
+  double qc_const[9], qc_fix[9];
+  double w_const, w_fix, eps_const;
+};
+
+template <typename IO>
+struct KWeights {
+  const IO* qc; long long qc_sb, qc_st;
+  const IO* w;  long long w_sb, w_st;
+  const IO* eps; long long e_sb, e_st;
+};
+
+enum : int { FLAG_NONHOLONOMIC = 1, FLAG_VEL_LIMITS = 2, FLAG_Q_FULL = 4 };
+
+__device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
+
+template <typename IO> __device__ __forceinline__ double ldg_d(const IO* p) { return (double)__ldg(p); }
+
+// ---------------------------------------------------------------------------
+// SDF bilinear lookup (utils/sdf_utils.py:57-94)
+// ---------------------------------------------------------------------------
+struct SdfSample { double dist, Jx, Jy; };   // J as returned by bilinear_interpolate
+
+template <typename IO>
+__device__ __forceinline__ SdfSample sdf_bilinear(const IO* __restrict__ sdf, int H, int W,
+                                                  double orig_x, double orig_y, double res,
+                                                  double x, double y) {
+  // px = orig_x + x / res ; py = orig_y - y / res   (true divisions, reference order)
+  const double px = __dadd_rn(orig_x, __ddiv_rn(x, res));
+  const double py = __dsub_rn(orig_y, __ddiv_rn(y, res));
+  const double fx = floor(px), fy = floor(py);
+  // floor -> +1 -> clamp to the image (sdf_utils.py:64-72), done in double so huge values cannot overflow
+  const double wm = (double)(W - 1), hm = (double)(H - 1);
+  const double x1d = fmin(fmax(fx, 0.0), wm), x2d = fmin(fmax(fx + 1.0, 0.0), wm);
+  const double y1d = fmin(fmax(fy, 0.0), hm), y2d = fmin(fmax(fy + 1.0, 0.0), hm);
+  const int x1 = (int)x1d, x2 = (int)x2d, y1 = (int)y1d, y2 = (int)y2d;
+  const IO* r1 = sdf + (long long)y1 * W;
+  const IO* r2 = sdf + (long long)y2 * W;
+  const double v11 = ldg_d(r1 + x1), v21 = ldg_d(r1 + x2);
+  const double v12 = ldg_d(r2 + x1), v22 = ldg_d(r2 + x2);
+  // weights from the CLAMPED indices (:81-89)
+  const double ax = __dsub_rn(x2d, px), bx = __dsub_rn(px, x1d);
+  const double ay = __dsub_rn(y2d, py), by = __dsub_rn(py, y1d);
+  // dist = wa*v11 + wb*v21 + wc*v12 + wd*v22, separately rounded like the tensor ops (:90)
+  const double wa = __dmul_rn(ax, ay), wb = __dmul_rn(bx, ay), wc = __dmul_rn(ax, by), wd = __dmul_rn(bx, by);
+  SdfSample s;
+  s.dist = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(wa, v11), __dmul_rn(wb, v21)), __dmul_rn(wc, v12)),
+                     __dmul_rn(wd, v22));
+  // J[:, :, 0] = -1*(wja*(v21-v11) + wjb*(v22-v12))/res ; J[:, :, 1] = (wjc*(v12-v11) + wjd*(v22-v21))/res  (:93-94)
+  const double gx = __dadd_rn(__dmul_rn(ay, __dsub_rn(v21, v11)), __dmul_rn(by, __dsub_rn(v22, v12)));
+  const double gy = __dadd_rn(__dmul_rn(ax, __dsub_rn(v12, v11)), __dmul_rn(bx, __dsub_rn(v22, v21)));
+  s.Jx = __ddiv_rn(-gx, res);
+  s.Jy = __ddiv_rn(gy, res);
+  return s;
+}
+
+// Hinge (obstacle_cost.py:30-37): c = (dist <= eps_tot) ? eps_tot - dist : 0 ; H_e = (dist <= eps_tot) ? -J : 0
+struct ObsTerm { double c, hx, hy; };
+__device__ __forceinline__ ObsTerm hinge(const SdfSample& s, double eps_tot) {
+  ObsTerm o;
+  const bool active = s.dist <= eps_tot;
+  o.c = active ? (eps_tot - s.dist) : 0.0;
+  o.hx = active ? -s.Jx : 0.0;
+  o.hy = active ? -s.Jy : 0.0;
+  return o;
+}
+
+// ---------------------------------------------------------------------------
+// GP prior inverse covariance for factor i (gp_factor.py:65-73) or given in full (plan_layer.py:90)
+// ---------------------------------------------------------------------------
+template <int DOF, typename IO>
+__device__ __forceinline__ void load_qinv(const KParams& P, const KWeights<IO>& Wt, int b, int i, double (&Q)[2 * DOF][2 * DOF]) {
+  constexpr int D = 2 * DOF;
+  if (P.flags & FLAG_Q_FULL) {
+    const IO* q = Wt.qc + (long long)b * Wt.qc_sb + (long long)i * Wt.qc_st;
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+      for (int c = 0; c < D; ++c) Q[a][c] = ldg_d(q + a * D + c);
+    return;
+  }
+  double C[DOF][DOF];
+  if (Wt.qc != nullptr) {
+    const IO* q = Wt.qc + (long long)b * Wt.qc_sb + (long long)i * Wt.qc_st;
+#pragma unroll
+    for (int a = 0; a < DOF; ++a)
+#pragma unroll
+      for (int c = 0; c < DOF; ++c) C[a][c] = ldg_d(q + a * DOF + c);
+  } else {
+#pragma unroll
+    for (int a = 0; a < DOF; ++a)
+#pragma unroll
+      for (int c = 0; c < DOF; ++c) C[a][c] = P.qc_const[a * DOF + c];
+  }
+#pragma unroll
+  for (int a = 0; a < DOF; ++a)
+#pragma unroll
+    for (int c = 0; c < DOF; ++c) {
+      Q[a][c] = P.qa * C[a][c];
+      Q[a][c + DOF] = P.qb * C[a][c];
+      Q[a + DOF][c] = P.qb * C[a][c];
+      Q[a + DOF][c + DOF] = P.qc * C[a][c];
+    }
+}
+
+template <int DOF>
+__device__ __forceinline__ void fixed_qinv(const KParams& P, double (&Q)[2 * DOF][2 * DOF]) {
+#pragma unroll
+  for (int a = 0; a < DOF; ++a)
+#pragma unroll
+    for (int c = 0; c < DOF; ++c) {
+      const double v = P.qc_fix[a * DOF + c];
+      Q[a][c] = P.qa * v;
+      Q[a][c + DOF] = P.qb * v;
+      Q[a + DOF][c] = P.qb * v;
+      Q[a + DOF][c + DOF] = P.qc * v;
+    }
+}
+
+// g = th_next - Phi th   (gp_factor.py:105), Phi = [[I, dt I],[0, I]]
+template <int DOF>
+__device__ __forceinline__ void gp_residual(const double (&th)[2 * DOF], const double (&thn)[2 * DOF], double dt,
+                                            double (&g)[2 * DOF]) {
+#pragma unroll
+  for (int a = 0; a < DOF; ++a) {
+    g[a] = thn[a] - (th[a] + dt * th[a + DOF]);
+    g[a + DOF] = thn[a + DOF] - th[a + DOF];
+  }
+}
+
+template <int D>
+__device__ __forceinline__ double quad_form(const double (&Q)[D][D], const double (&g)[D]) {
+  double s = 0.0;
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+    double row = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) row += Q[a][c] * g[c];
+    s += g[a] * row;
+  }
+  return s;
+}
+
+// ---------------------------------------------------------------------------
+// One state's share of the normal equations.
+// ---------------------------------------------------------------------------
+template <int DOF>
+struct NodeOut {
+  static constexpr int D = 2 * DOF;
+  double Dm[D][D];   // full symmetric diagonal block Lambda_tt (includes reg)
+  double Um[D][D];   // Lambda_{t,t+1} (zero for t == T-1)
+  double r[D];
+  double err, err_ext;        // this state's 0.5 e^T K e contributions (NOT yet divided by M)
+  double e_sg, e_gp, e_obs;   // unweighted: 0.5|e_prior|^2, 0.5|g_t|^2 (t<T-1), 0.5 c_t^2
+  double obs_c, obs_hx, obs_hy;
+};
+
+// th_prev / th_next are ignored at the trajectory ends.
+template <int DOF, typename IO>
+__device__ __forceinline__ void assemble_node(const KParams& P, const KWeights<IO>& Wt, int b, int t,
+                                              const double (&thp)[2 * DOF], const double (&th)[2 * DOF],
+                                              const double (&thn)[2 * DOF],
+                                              const IO* __restrict__ start_b, const IO* __restrict__ goal_b,
+                                              const IO* __restrict__ sdf_b, NodeOut<DOF>& o) {
+  constexpr int D = 2 * DOF;
+  const int T = P.T;
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+    o.r[a] = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      o.Dm[a][c] = (a == c) ? P.reg : 0.0;
+      o.Um[a][c] = 0.0;
+    }
+  }
+  o.err = 0.0; o.err_ext = 0.0; o.e_sg = 0.0; o.e_gp = 0.0;
+
+  // ---- start / goal priors (prior_factor.py:15-18; K = I/K^2, plan_layer.py:64-68) ----
+  if (t == 0) {
+    double s2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      const double e = ldg_d(start_b + a) - th[a];
+      o.Dm[a][a] += P.ks;
+      o.r[a] += P.ks * e;
+      s2 += e * e;
+    }
+    o.err += 0.5 * P.ks * s2; o.err_ext += 0.5 * P.ks * s2; o.e_sg += 0.5 * s2;
+  }
+  if (t == T - 1) {
+    double s2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      const double e = ldg_d(goal_b + a) - th[a];
+      o.Dm[a][a] += P.kg;
+      o.r[a] += P.kg * e;
+      s2 += e * e;
+    }
+    o.err += 0.5 * P.kg * s2; o.err_ext += 0.5 * P.kg * s2; o.e_sg += 0.5 * s2;
+  }
+
+  // ---- GP factor t (between t and t+1): H1 = Phi on state t, H2 = -I on state t+1 ----
+  if (t < T - 1) {
+    double Q[D][D], g[D];
+    load_qinv<DOF, IO>(P, Wt, b, t, Q);
+    gp_residual<DOF>(th, thn, P.dt, g);
+    // PtQ = Phi^T Q : rows a<DOF: Q[a][:], rows a>=DOF: dt*Q[a-DOF][:] + Q[a][:]
+    double PtQ[D][D];
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+#pragma unroll
+      for (int a = 0; a < DOF; ++a) {
+        PtQ[a][c] = Q[a][c];
+        PtQ[a + DOF][c] = P.dt * Q[a][c] + Q[a + DOF][c];
+      }
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      double ra = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        ra += PtQ[a][c] * g[c];
+        o.Um[a][c] = -PtQ[a][c];
+      }
+      o.r[a] += ra;
+      // (Phi^T Q Phi)[a][c] : c<DOF: PtQ[a][c] ; c>=DOF: dt*PtQ[a][c-DOF] + PtQ[a][c]
+#pragma unroll
+      for (int c = 0; c < DOF; ++c) {
+        o.Dm[a][c] += PtQ[a][c];
+        o.Dm[a][c + DOF] += P.dt * PtQ[a][c] + PtQ[a][c + DOF];
+      }
+    }
+    o.err += 0.5 * quad_form<D>(Q, g);
+    double Qf[D][D];
+    fixed_qinv<DOF>(P, Qf);
+    o.err_ext += 0.5 * quad_form<D>(Qf, g);
+    double g2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) g2 += g[a] * g[a];
+    o.e_gp = 0.5 * g2;
+  }
+  // ---- GP factor t-1 (between t-1 and t): this state carries H2 = -I ----
+  if (t > 0) {
+    double Q[D][D], g[D];
+    load_qinv<DOF, IO>(P, Wt, b, t - 1, Q);
+    gp_residual<DOF>(thp, th, P.dt, g);
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      double ra = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        ra += Q[a][c] * g[c];
+        o.Dm[a][c] += Q[a][c];
+      }
+      o.r[a] -= ra;
+    }
+  }
+
+  // ---- obstacle factor (obstacle_factor.py:35-40; one sphere centred at (x, y), J_fk = [I2 0]) ----
+  {
+    const double eps = (Wt.eps != nullptr) ? ldg_d(Wt.eps + (long long)b * Wt.e_sb + (long long)t * Wt.e_st) : P.eps_const;
+    const double w = (Wt.w != nullptr) ? ldg_d(Wt.w + (long long)b * Wt.w_sb + (long long)t * Wt.w_st) : P.w_const;
+    const double eps_tot = __dadd_rn(eps, P.r_sphere);
+    const SdfSample s = sdf_bilinear<IO>(sdf_b, P.H, P.W, P.orig_x, P.orig_y, P.res, th[0], th[1]);
+    const ObsTerm ob = hinge(s, eps_tot);
+    o.Dm[0][0] += w * ob.hx * ob.hx;
+    o.Dm[0][1] += w * ob.hx * ob.hy;
+    o.Dm[1][0] += w * ob.hx * ob.hy;
+    o.Dm[1][1] += w * ob.hy * ob.hy;
+    o.r[0] += w * ob.hx * ob.c;
+    o.r[1] += w * ob.hy * ob.c;
+    o.err += 0.5 * w * ob.c * ob.c;
+    o.err_ext += 0.5 * P.w_fix * ob.c * ob.c;
+    o.e_obs = 0.5 * ob.c * ob.c;
+    o.obs_c = ob.c; o.obs_hx = ob.hx; o.obs_hy = ob.hy;
+  }
+
+  // ---- custom unary factors ----
+  if constexpr (DOF == 3) {
+    if (P.flags & FLAG_NONHOLONOMIC) {
+      // nonholonomic_factor.py:16-30, state (x, y, h, vx, vy, w); Jacobian row reproduced literally
+      double sh, ch;
+      sincos(th[2], &sh, &ch);
+      const double e = th[4] * ch - th[3] * sh;
+      double n[D] = {0.0, 0.0, -th[4] * sh + th[3] * ch, -sh, ch, 0.0};
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) o.Dm[a][c] += P.kd * n[a] * n[c];
+        o.r[a] += P.kd * n[a] * e;
+      }
+      o.err += 0.5 * P.kd * e * e;
+      o.err_ext += 0.5 * P.kd * e * e;
+    }
+  }
+  if constexpr (DOF == 2) {
+    if (P.flags & FLAG_VEL_LIMITS) {
+      // velocity_limit_factor.py:17-29: active when |v| >= limit; H = -sign(v) on the velocity entry
+      const double vx = th[2], vy = th[3];
+      const bool ax = fabs(vx) >= P.vx_lim, ay = fabs(vy) >= P.vy_lim;
+      const double cx = ax ? fabs(vx) - P.vx_lim : 0.0, cy = ay ? fabs(vy) - P.vy_lim : 0.0;
+      const double sx = ax ? -((vx > 0.0) - (vx < 0.0)) : 0.0, sy = ay ? -((vy > 0.0) - (vy < 0.0)) : 0.0;
+      o.Dm[2][2] += P.kv * sx * sx;
+      o.Dm[3][3] += P.kv * sy * sy;
+      o.r[2] += P.kv * sx * cx;
+      o.r[3] += P.kv * sy * cy;
+      o.err += 0.5 * P.kv * (cx * cx + cy * cy);
+      o.err_ext += 0.5 * P.kv * (cx * cx + cy * cy);
+    }
+  }
+}
+
+}  // namespace dgpmp2

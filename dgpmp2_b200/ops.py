@@ -1,0 +1,207 @@
+"""Tensor-level entry points: torch CUDA tensors in, torch CUDA tensors out, all compute in
+libdgpmp2_b200.so through the C ABI.  These are what the planner / factor classes call.
+"""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import CParams, check, load, make_weights, ptr, stream_ptr, suffix
+
+
+def _prep(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.Dgpmp2Error('%s must be a CUDA tensor (no CPU path)' % name)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _sdf3(sdf: torch.Tensor, B: int) -> Tuple[torch.Tensor, int]:
+    """(B,1,H,W) / (B,H,W) / (1,H,W) / (H,W) -> contiguous (n,H,W) and problem stride in elements."""
+    if sdf.dim() == 4:
+        sdf = sdf[:, 0]
+    if sdf.dim() == 2:
+        sdf = sdf.unsqueeze(0)
+    if sdf.dim() != 3 or sdf.shape[0] not in (1, B):
+        raise ValueError('sdf must be (B,1,H,W), got %s' % (tuple(sdf.shape),))
+    sdf = sdf.contiguous()
+    stride = 0 if (sdf.shape[0] == 1 and B > 1) else sdf.shape[1] * sdf.shape[2]
+    return sdf, stride
+
+
+def _common(p: CParams, th, start, goal, sdf):
+    _lib.require_cuda()
+    B, T, d = th.shape
+    if d != 2 * p.dof or T != p.T:
+        raise ValueError('trajectory shape %s does not match params (T=%d, d=%d)' % (tuple(th.shape), p.T, 2 * p.dof))
+    dtype = th.dtype
+    th = _prep(th, dtype, 'th')
+    start = _prep(start, dtype, 'start').reshape(B, d) if start is not None else None
+    goal = _prep(goal, dtype, 'goal').reshape(B, d) if goal is not None else None
+    sdf, sdf_sb = _sdf3(_prep(sdf, dtype, 'sdf'), B)
+    p.B = B
+    p.H, p.W = int(sdf.shape[1]), int(sdf.shape[2])
+    p.sdf_stride_b = sdf_sb
+    return th, start, goal, sdf
+
+
+def _weights(p: CParams, dtype, qc_inv, w_obs, eps, B, T):
+    if qc_inv is None and w_obs is None and eps is None:
+        return None, []
+    blk = 2 * p.dof if (p.flags & _lib.FLAG_Q_FULL) else p.dof
+    qc = _prep_w(qc_inv, dtype)
+    wo = _prep_w(w_obs, dtype)
+    ep = _prep_w(eps, dtype)
+    w, keep = make_weights(qc, wo, ep, B, T, blk)
+    return ctypes.byref(w), keep + [w]
+
+
+def _prep_w(t, dtype):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.Dgpmp2Error('weights must be CUDA tensors')
+    return t if t.dtype == dtype else t.to(dtype)
+
+
+def gn_step(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, want_status=True):
+    """One batched GN iteration. Returns dth (B,T,d), err (B,), err_ext (B,), status (B,) int32 or None."""
+    th, start, goal, sdf = _common(p, th, start, goal, sdf)
+    B, T, d = th.shape
+    dth = torch.empty_like(th)
+    err = torch.empty(B, dtype=th.dtype, device=th.device)
+    err_ext = torch.empty_like(err)
+    status = torch.empty(B, dtype=torch.int32, device=th.device) if want_status else None
+    wref, keep = _weights(p, th.dtype, qc_inv, w_obs, eps, B, T)
+    fn = getattr(load(), 'dgpmp2_gn_step_' + suffix(th.dtype))
+    check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(sdf), wref, ptr(dth), ptr(err), ptr(err_ext),
+             ptr(status), stream_ptr()))
+    return dth, err, err_ext, status
+
+
+def gn_solve(p: CParams, th, start, goal, sdf, max_iters: int, tol_delta: float, qc_inv=None, w_obs=None, eps=None):
+    """Persistent solve to convergence. Returns th_final, iters, err_per_iter (B,max_iters; NaN beyond iters),
+    err_ext_per_iter, err_final, err_ext_final, status."""
+    th, start, goal, sdf = _common(p, th, start, goal, sdf)
+    B, T, d = th.shape
+    dev, dt = th.device, th.dtype
+    th_final = torch.empty_like(th)
+    iters = torch.empty(B, dtype=torch.int32, device=dev)
+    epi = torch.full((B, int(max_iters)), float('nan'), dtype=dt, device=dev)
+    eepi = torch.full((B, int(max_iters)), float('nan'), dtype=dt, device=dev)
+    ef = torch.empty(B, dtype=dt, device=dev)
+    eef = torch.empty(B, dtype=dt, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    wref, keep = _weights(p, dt, qc_inv, w_obs, eps, B, T)
+    fn = getattr(load(), 'dgpmp2_gn_solve_' + suffix(dt))
+    check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(sdf), wref, int(max_iters), float(tol_delta),
+             ptr(th_final), ptr(iters), ptr(epi), ptr(eepi), ptr(ef), ptr(eef), ptr(status), stream_ptr()))
+    return th_final, iters, epi, eepi, ef, eef, status
+
+
+def errors(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None):
+    """Factor sweep. Returns err, err_ext, err_sg, err_gp, err_obs, each (B,)."""
+    th, start, goal, sdf = _common(p, th, start, goal, sdf)
+    B, T, d = th.shape
+    outs = [torch.empty(B, dtype=th.dtype, device=th.device) for _ in range(5)]
+    wref, keep = _weights(p, th.dtype, qc_inv, w_obs, eps, B, T)
+    fn = getattr(load(), 'dgpmp2_errors_' + suffix(th.dtype))
+    check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(sdf), wref, *[ptr(o) for o in outs], stream_ptr()))
+    return tuple(outs)
+
+
+def factors(p: CParams, th, sdf=None, eps=None, want_gp=True, want_obs=True, want_custom=False):
+    """Stand-alone factor outputs: gp_err (B,T-1,d), obs_cost (B,T), obs_H (B,T,d), cust_err, cust_H (or None)."""
+    _lib.require_cuda()
+    B, T, d = th.shape
+    dt, dev = th.dtype, th.device
+    th = _prep(th, dt, 'th')
+    p.B = B
+    sdf3 = None
+    if want_obs:
+        sdf3, sb = _sdf3(_prep(sdf, dt, 'sdf'), B)
+        p.H, p.W, p.sdf_stride_b = int(sdf3.shape[1]), int(sdf3.shape[2]), sb
+    gp = torch.empty(B, T - 1, d, dtype=dt, device=dev) if want_gp else None
+    oc = torch.empty(B, T, dtype=dt, device=dev) if want_obs else None
+    oh = torch.empty(B, T, d, dtype=dt, device=dev) if want_obs else None
+    ce = ch = None
+    if want_custom and (p.flags & _lib.FLAG_NONHOLONOMIC):
+        ce = torch.empty(B, T, dtype=dt, device=dev)
+        ch = torch.empty(B, T, d, dtype=dt, device=dev)
+    elif want_custom and (p.flags & _lib.FLAG_VEL_LIMITS):
+        ce = torch.empty(B, T, 2, dtype=dt, device=dev)
+        ch = torch.empty(B, T, 2, d, dtype=dt, device=dev)
+    wref, keep = _weights(p, dt, None, None, eps, B, T)
+    fn = getattr(load(), 'dgpmp2_factors_' + suffix(dt))
+    check(fn(ctypes.byref(p), ptr(th), ptr(sdf3), wref, ptr(gp), ptr(oc), ptr(oh), ptr(ce), ptr(ch), stream_ptr()))
+    return gp, oc, oh, ce, ch
+
+
+def sdf_lookup(sdf, pts, res: float, x_lo: float, y_lo: float):
+    """bilinear_interpolate: sdf (B,H,W), pts (B,N,2) -> dist (B,N,1), J (B,N,2)."""
+    _lib.require_cuda()
+    dt = pts.dtype
+    B, N, _ = pts.shape
+    pts = _prep(pts, dt, 'pts')
+    sdf3, sb = _sdf3(_prep(sdf, dt, 'sdf'), B)
+    dist = torch.empty(B, N, 1, dtype=dt, device=pts.device)
+    J = torch.empty(B, N, 2, dtype=dt, device=pts.device)
+    fn = getattr(load(), 'dgpmp2_sdf_lookup_' + suffix(dt))
+    check(fn(ptr(sdf3), B, int(sdf3.shape[1]), int(sdf3.shape[2]), sb, ptr(pts), N, float(res), float(x_lo),
+             float(y_lo), ptr(dist), ptr(J), stream_ptr()))
+    return dist, J
+
+
+def band(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None):
+    """Information band in float64: D (B,T,d,d), U (B,T-1,d,d), r (B,T,d)."""
+    th, start, goal, sdf = _common(p, th, start, goal, sdf)
+    B, T, d = th.shape
+    D = torch.empty(B, T, d, d, dtype=torch.float64, device=th.device)
+    U = torch.empty(B, T - 1, d, d, dtype=torch.float64, device=th.device)
+    r = torch.empty(B, T, d, dtype=torch.float64, device=th.device)
+    wref, keep = _weights(p, th.dtype, qc_inv, w_obs, eps, B, T)
+    fn = getattr(load(), 'dgpmp2_band_' + suffix(th.dtype))
+    check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(sdf), wref, ptr(D), ptr(U), ptr(r), stream_ptr()))
+    return D, U, r
+
+
+class HostStepper:
+    """End-to-end GN step on HOST tensors through dgpmp2_gn_step_host_* (the e2e path of bench.py
+    and of the planner when it is handed CPU tensors).  Owns the device workspace and pinned
+    output buffers for one problem shape."""
+
+    def __init__(self, p: CParams, dtype=torch.float32, device=None):
+        _lib.require_cuda()
+        self.p = p
+        self.dtype = dtype
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        nbytes = ctypes.c_size_t(0)
+        es = 4 if dtype == torch.float32 else 8
+        check(load().dgpmp2_host_step_workspace_bytes(ctypes.byref(p), es, ctypes.byref(nbytes)))
+        self.ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        B, T, d = p.B, p.T, 2 * p.dof
+        self.dth = torch.empty(B, T, d, dtype=dtype).pin_memory()
+        self.err = torch.empty(B, dtype=dtype).pin_memory()
+        self.err_ext = torch.empty(B, dtype=dtype).pin_memory()
+        self.status = torch.empty(B, dtype=torch.int32).pin_memory()
+        self.h2d_bytes = (B * T * d + 2 * B * d) * es
+        self.sdf_bytes = (p.H * p.W if p.sdf_stride_b == 0 else p.sdf_stride_b * B) * es
+        self.d2h_bytes = (B * T * d + 2 * B) * es + 4 * B
+
+    def step(self, th, start, goal, sdf, sdf_resident=False):
+        """Host tensors (contiguous, ideally pinned) -> (dth, err, err_ext, status) pinned host tensors.
+        Synchronous: returns when the results are in host memory."""
+        fn = getattr(load(), 'dgpmp2_gn_step_host_' + suffix(self.dtype))
+        check(fn(ctypes.byref(self.p), ptr(th), ptr(start), ptr(goal), ptr(sdf), ptr(self.dth), ptr(self.err),
+                 ptr(self.err_ext), ptr(self.status), ctypes.c_void_p(self.ws.data_ptr()), self.ws.numel(),
+                 1 if sdf_resident else 0, stream_ptr()))
+        return self.dth, self.err, self.err_ext, self.status
+
+
+def launch_shape(p: CParams, dtype=torch.float32):
+    np_, thr, smem, grid = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    check(load().dgpmp2_gn_step_launch_shape(ctypes.byref(p), 4 if dtype == torch.float32 else 8, ctypes.byref(np_),
+                                             ctypes.byref(thr), ctypes.byref(smem), ctypes.byref(grid)))
+    return {'problems_per_cta': np_.value, 'threads': thr.value, 'smem_bytes': smem.value, 'grid': grid.value}
