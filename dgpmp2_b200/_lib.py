@@ -128,6 +128,7 @@ def make_params(B, T, dof, H, W, x_lims, y_lims, total_time_sec, r_sphere, K_s, 
     """Fill struct dgpmp2_params from planner constants, computing the derived scalars in
     double precision the way the reference computes them (file:line in the header)."""
     p = CParams()
+    p.x_hi, p.y_hi = float(x_lims[1]), float(y_lims[1])     # python-side only (res depends on the SDF width)
     p.B, p.T, p.dof, p.H, p.W = int(B), int(T), int(dof), int(H), int(W)
     flags = 0
     if non_holonomic:
@@ -161,6 +162,12 @@ def make_params(B, T, dof, H, W, x_lims, y_lims, total_time_sec, r_sphere, K_s, 
     p.w_obs = p.w_obs_fix if w_obs_static is None else _as_float(w_obs_static)
     p.eps = _as_float(epsilon_dist) if eps_static is None else _as_float(eps_static)
     return p
+
+
+def set_sdf_shape(p: CParams, H: int, W: int, stride_b: int):
+    """Record the SDF geometry of this call; the cell size follows the SDF WIDTH (obstacle_cost.py:34)."""
+    p.H, p.W, p.sdf_stride_b = int(H), int(W), int(stride_b)
+    p.res = (p.x_hi - p.x_lo) / (int(W))
 
 
 def num_factor_rows(p: CParams) -> int:

@@ -42,8 +42,7 @@ def _common(p: CParams, th, start, goal, sdf):
     goal = _prep(goal, dtype, 'goal').reshape(B, d) if goal is not None else None
     sdf, sdf_sb = _sdf3(_prep(sdf, dtype, 'sdf'), B)
     p.B = B
-    p.H, p.W = int(sdf.shape[1]), int(sdf.shape[2])
-    p.sdf_stride_b = sdf_sb
+    _lib.set_sdf_shape(p, sdf.shape[1], sdf.shape[2], sdf_sb)
     return th, start, goal, sdf
 
 
@@ -122,7 +121,7 @@ def factors(p: CParams, th, sdf=None, eps=None, want_gp=True, want_obs=True, wan
     sdf3 = None
     if want_obs:
         sdf3, sb = _sdf3(_prep(sdf, dt, 'sdf'), B)
-        p.H, p.W, p.sdf_stride_b = int(sdf3.shape[1]), int(sdf3.shape[2]), sb
+        _lib.set_sdf_shape(p, sdf3.shape[1], sdf3.shape[2], sb)
     gp = torch.empty(B, T - 1, d, dtype=dt, device=dev) if want_gp else None
     oc = torch.empty(B, T, dtype=dt, device=dev) if want_obs else None
     oh = torch.empty(B, T, d, dtype=dt, device=dev) if want_obs else None

@@ -183,7 +183,7 @@ def main():
 
     # 6b. forward on a problem that converges before max_iters (tol_delta raised) + a 3-problem batch run per sample
     P2 = dict(YAML)
-    P2.update(tol_delta=0.05, max_iters=30)
+    P2.update(tol_delta=1.0, max_iters=30)
     th, s, g, sdf = synth(3, 32, 64, seed=9)
     th, s, g, sdf = r32(th), r32(s), r32(g), r32(sdf)
     planner = ref_harness.make_reference_planner(1, 32, P2, lims, lims)
@@ -199,7 +199,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, 'forward_B3_T32.npz'), th=th.numpy().astype(np.float32),
                         start=s.numpy().astype(np.float32), goal=g.numpy().astype(np.float32),
                         sdf=sdf.numpy().astype(np.float32), x_lims=np.array(lims), y_lims=np.array(lims), T=32,
-                        max_iters=30, tol_delta=0.05, fwd_th_final=th_final.numpy(), fwd_err_init=np.array(err_init),
+                        max_iters=30, tol_delta=1.0, fwd_th_final=th_final.numpy(), fwd_err_init=np.array(err_init),
                         fwd_err_final=np.array(err_final), fwd_err_per_iter=epi, fwd_err_ext_per_iter=eepi,
                         fwd_iters=np.array(k))
     print('forward_B3_T32: iters=%s' % (k,))
