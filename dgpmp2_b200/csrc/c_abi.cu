@@ -57,7 +57,43 @@ KParams make_kparams(const dgpmp2_params* p) {
   k.kd = p->kd_inv2; k.kv = p->kv_inv2; k.vx_lim = p->vx_lim; k.vy_lim = p->vy_lim;
   for (int i = 0; i < 9; ++i) { k.qc_const[i] = p->qc_inv[i]; k.qc_fix[i] = p->qc_inv_fix[i]; }
   k.w_const = p->w_obs; k.w_fix = p->w_obs_fix; k.eps_const = p->eps;
+  // constant GP blocks for the static case: Q = [[qa C, qb C],[qb C, qc C]], Phi = [[I, dt I],[0, I]]
+  const int dof = p->dof;
+  auto kron = [&](const double* C, double* Q) {
+    for (int a = 0; a < dof; ++a)
+      for (int c = 0; c < dof; ++c) {
+        const double v = C[a * dof + c];
+        Q[a * d + c] = k.qa * v;
+        Q[a * d + c + dof] = k.qb * v;
+        Q[(a + dof) * d + c] = k.qb * v;
+        Q[(a + dof) * d + c + dof] = k.qc * v;
+      }
+  };
+  kron(k.qc_const, k.Qs);
+  kron(k.qc_fix, k.Qf);
+  for (int c = 0; c < d; ++c)
+    for (int a = 0; a < dof; ++a) {
+      k.PQs[a * d + c] = k.Qs[a * d + c];
+      k.PQs[(a + dof) * d + c] = k.dt * k.Qs[a * d + c] + k.Qs[(a + dof) * d + c];
+    }
+  for (int a = 0; a < d; ++a)
+    for (int c = 0; c < dof; ++c) {
+      k.PQPs[a * d + c] = k.PQs[a * d + c];
+      k.PQPs[a * d + c + dof] = k.dt * k.PQs[a * d + c] + k.PQs[a * d + c + dof];
+    }
+  k.static_gp = 0;   // set by the caller once the weights are known
+  k.ext_same = 0;
   return k;
+}
+
+// static_gp: no per-(b,t) Qc^-1 and not Q_FULL.  ext_same: additionally every weight equals its
+// constructor-time value, so err_ext == err.
+template <typename IO>
+void finish_kparams(KParams& k, const KWeights<IO>& kw) {
+  k.static_gp = (kw.qc == nullptr && !(k.flags & DGPMP2_FLAG_Q_FULL)) ? 1 : 0;
+  bool same = k.static_gp && kw.w == nullptr && k.w_const == k.w_fix;
+  for (int i = 0; i < 9 && same; ++i) same = (k.qc_const[i] == k.qc_fix[i]);
+  k.ext_same = same ? 1 : 0;
 }
 
 template <typename IO>
@@ -72,33 +108,52 @@ KWeights<IO> make_kweights(const dgpmp2_weights* w) {
   return k;
 }
 
-struct LaunchShape { int np, threads, smem, grid; };
+struct LaunchShape { int nn, lpn, np, tpp, threads, smem, grid; };
 
-// Problems per CTA: aim for ~256 threads (one per trajectory state) and <= half an SM's shared
-// memory so that two CTAs are co-resident and one CTA's sparse BCR levels overlap the other's
-// dense ones.  DGPMP2_NP overrides (tuning only).
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  if (e == nullptr) return dflt;
+  const int v = atoi(e);
+  return v > 0 ? v : dflt;
+}
+
+// Node slots per CTA (compile-time NN), problems per CTA, threads per problem.
+// One problem per CTA once T >= 33 (the CTA-wide barriers of the BCR then only couple the warps
+// of one problem and the scheduler overlaps different problems' sparse and dense levels);
+// several short problems share a CTA so that it still fills a few warps.
 template <int D, typename IO>
 int choose_shape(int B, int T, bool solve, LaunchShape& s) {
-  const int max_threads = (D == 4) ? 512 : 256;
-  int np = 256 / T;
+  int nn;
+  if (T <= 64) nn = 64;
+  else if (T <= 128) nn = 128;
+  else if (T <= 256) nn = 256;
+  else if (T <= 512 && D == 4) nn = 512;
+  else return DGPMP2_ERR_UNSUPPORTED;
+  const int lpn = (env_int("DGPMP2_LPN", 4) == 2) ? 2 : 4;
+  const int cap = (D == 4) ? 512 : 384;
+  int max_threads = lpn * nn / 2;
+  max_threads = (max_threads < cap) ? ((max_threads + 31) / 32 * 32) : cap;
+  int np = nn / T;
   if (np < 1) np = 1;
-  if (const char* e = getenv("DGPMP2_NP")) { const int v = atoi(e); if (v > 0) np = v; }
+  np = env_int("DGPMP2_NP", np);
+  if (np > nn / T) np = nn / T;
   if (np > B) np = B;
   if (np < 1) np = 1;
-  const size_t half = kSmemLimit / 2 - 1024;
-  while (np > 1 && StepSmem<D, IO>::bytes(np, T, solve) > half) --np;
-  if (getenv("DGPMP2_NP")) {   // explicit override may use the whole SM
-    np = atoi(getenv("DGPMP2_NP"));
-    if (np > B) np = B;
-    if (np < 1) np = 1;
-    while (np > 1 && StepSmem<D, IO>::bytes(np, T, solve) > (size_t)kSmemLimit) --np;
+  int tpp = lpn * ((T + 1) / 2);
+  if (np * tpp > max_threads) tpp = (max_threads / np) / lpn * lpn;
+  if (tpp < lpn) return DGPMP2_ERR_UNSUPPORTED;
+  s.nn = nn; s.lpn = lpn; s.np = np; s.tpp = tpp;
+  s.threads = (np * tpp + 31) / 32 * 32;
+  size_t bytes = 0;
+  switch (nn) {
+    case 64: bytes = StepSmem<D, 64, IO>::bytes(solve); break;
+    case 128: bytes = StepSmem<D, 128, IO>::bytes(solve); break;
+    case 256: bytes = StepSmem<D, 256, IO>::bytes(solve); break;
+    default: bytes = StepSmem<D, 512, IO>::bytes(solve); break;
   }
-  const size_t bytes = StepSmem<D, IO>::bytes(np, T, solve);
   if (bytes > (size_t)kSmemLimit) return DGPMP2_ERR_UNSUPPORTED;
-  int threads = ((np * T + 31) / 32) * 32;
-  if (threads > max_threads) threads = max_threads;
-  if (const char* e = getenv("DGPMP2_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= max_threads) threads = (v / 32) * 32; }
-  s.np = np; s.threads = threads; s.smem = (int)bytes; s.grid = (B + np - 1) / np;
+  s.smem = (int)bytes;
+  s.grid = (B + np - 1) / np;
   return DGPMP2_OK;
 }
 
@@ -108,18 +163,40 @@ int allow_smem(K kernel, int bytes) {
   return DGPMP2_OK;
 }
 
+template <int DOF, int NN, int LPN, typename IO>
+int launch_step_nn(const LaunchShape& s, const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start,
+                   const IO* goal, const IO* sdf, IO* dth, IO* err, IO* err_ext, int32_t* status, cudaStream_t st) {
+  auto kern = gn_step_kernel<DOF, NN, LPN, IO>;
+  int rc = allow_smem(kern, s.smem);
+  if (rc != DGPMP2_OK) return rc;
+  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, s.np, s.tpp);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
+}
+
+template <int DOF, int LPN, typename IO>
+int launch_step_lpn(const LaunchShape& s, const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start,
+                    const IO* goal, const IO* sdf, IO* dth, IO* err, IO* err_ext, int32_t* status, cudaStream_t st) {
+  switch (s.nn) {
+    case 64: return launch_step_nn<DOF, 64, LPN, IO>(s, k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
+    case 128: return launch_step_nn<DOF, 128, LPN, IO>(s, k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
+    case 256: return launch_step_nn<DOF, 256, LPN, IO>(s, k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
+    default:
+      if constexpr (DOF == 2)
+        return launch_step_nn<DOF, 512, LPN, IO>(s, k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
+      else
+        return DGPMP2_ERR_UNSUPPORTED;
+  }
+}
+
 template <int DOF, typename IO>
 int launch_step(const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start, const IO* goal, const IO* sdf,
                 IO* dth, IO* err, IO* err_ext, int32_t* status, cudaStream_t st) {
   LaunchShape s;
   int rc = choose_shape<2 * DOF, IO>(k.B, k.T, false, s);
   if (rc != DGPMP2_OK) return rc;
-  auto kern = gn_step_kernel<DOF, IO>;
-  rc = allow_smem(kern, s.smem);
-  if (rc != DGPMP2_OK) return rc;
-  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, s.np);
-  CUDA_TRY(cudaGetLastError());
-  return DGPMP2_OK;
+  if (s.lpn == 2) return launch_step_lpn<DOF, 2, IO>(s, k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
+  return launch_step_lpn<DOF, 4, IO>(s, k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
 }
 
 template <typename IO>
@@ -129,11 +206,25 @@ int gn_step_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO
   if (rc != DGPMP2_OK) return rc;
   if (p->B == 0) return DGPMP2_OK;
   if (!th || !start || !goal || !sdf || !dth || !err || !err_ext) return DGPMP2_ERR_ARG;
-  const KParams k = make_kparams(p);
+  KParams k = make_kparams(p);
   const KWeights<IO> kw = make_kweights<IO>(w);
+  finish_kparams(k, kw);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dof == 2) return launch_step<2, IO>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
   return launch_step<3, IO>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
+}
+
+template <int DOF, int NN, int LPN, typename IO>
+int launch_solve_nn(const LaunchShape& s, const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start,
+                    const IO* goal, const IO* sdf, int max_iters, double tol, IO* th_final, int32_t* iters, IO* epi,
+                    IO* eepi, IO* ef, IO* eef, int32_t* status, cudaStream_t st) {
+  auto kern = gn_solve_kernel<DOF, NN, LPN, IO>;
+  int rc = allow_smem(kern, s.smem);
+  if (rc != DGPMP2_OK) return rc;
+  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, max_iters, tol, th_final, iters, epi, eepi, ef,
+                                          eef, status, s.np, s.tpp);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
 }
 
 template <int DOF, typename IO>
@@ -143,13 +234,23 @@ int launch_solve(const KParams& k, const KWeights<IO>& kw, const IO* th, const I
   LaunchShape s;
   int rc = choose_shape<2 * DOF, IO>(k.B, k.T, true, s);
   if (rc != DGPMP2_OK) return rc;
-  auto kern = gn_solve_kernel<DOF, IO>;
-  rc = allow_smem(kern, s.smem);
-  if (rc != DGPMP2_OK) return rc;
-  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, max_iters, tol, th_final, iters, epi, eepi, ef,
-                                          eef, status, s.np);
-  CUDA_TRY(cudaGetLastError());
-  return DGPMP2_OK;
+#define DGPMP2_SOLVE_CASE(NNV, LPNV) \
+  return launch_solve_nn<DOF, NNV, LPNV, IO>(s, k, kw, th, start, goal, sdf, max_iters, tol, th_final, iters, epi, eepi, ef, eef, status, st)
+  if (s.lpn == 2) {
+    switch (s.nn) {
+      case 64: DGPMP2_SOLVE_CASE(64, 2);
+      case 128: DGPMP2_SOLVE_CASE(128, 2);
+      case 256: DGPMP2_SOLVE_CASE(256, 2);
+      default: if constexpr (DOF == 2) { DGPMP2_SOLVE_CASE(512, 2); } else { return DGPMP2_ERR_UNSUPPORTED; }
+    }
+  }
+  switch (s.nn) {
+    case 64: DGPMP2_SOLVE_CASE(64, 4);
+    case 128: DGPMP2_SOLVE_CASE(128, 4);
+    case 256: DGPMP2_SOLVE_CASE(256, 4);
+    default: if constexpr (DOF == 2) { DGPMP2_SOLVE_CASE(512, 4); } else { return DGPMP2_ERR_UNSUPPORTED; }
+  }
+#undef DGPMP2_SOLVE_CASE
 }
 
 template <typename IO>
@@ -161,8 +262,9 @@ int gn_solve_impl(const dgpmp2_params* p, const IO* th, const IO* start, const I
   if (max_iters < 1) return DGPMP2_ERR_ARG;
   if (p->B == 0) return DGPMP2_OK;
   if (!th || !start || !goal || !sdf || !th_final || !iters) return DGPMP2_ERR_ARG;
-  const KParams k = make_kparams(p);
+  KParams k = make_kparams(p);
   const KWeights<IO> kw = make_kweights<IO>(w);
+  finish_kparams(k, kw);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dof == 2)
     return launch_solve<2, IO>(k, kw, th, start, goal, sdf, max_iters, tol, th_final, iters, epi, eepi, ef, eef, status, st);
@@ -176,8 +278,9 @@ int errors_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO*
   if (rc != DGPMP2_OK) return rc;
   if (p->B == 0) return DGPMP2_OK;
   if (!th || !start || !goal || !sdf) return DGPMP2_ERR_ARG;
-  const KParams k = make_kparams(p);
+  KParams k = make_kparams(p);
   const KWeights<IO> kw = make_kweights<IO>(w);
+  finish_kparams(k, kw);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int threads = ((p->T + 31) / 32) * 32;
   if (threads > 256) threads = 256;
@@ -226,8 +329,9 @@ int band_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO* g
   if (rc != DGPMP2_OK) return rc;
   if (p->B == 0) return DGPMP2_OK;
   if (!th || !start || !goal || !sdf || !D || !U || !r) return DGPMP2_ERR_ARG;
-  const KParams k = make_kparams(p);
+  KParams k = make_kparams(p);
   const KWeights<IO> kw = make_kweights<IO>(w);
+  finish_kparams(k, kw);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int g = grid_for((long long)p->B * p->T, 128);
   if (p->dof == 2) band_kernel<2, IO><<<g, 128, 0, st>>>(k, kw, th, start, goal, sdf, D, U, r);
@@ -412,7 +516,7 @@ int dgpmp2_gn_step_launch_shape(const dgpmp2_params* p, int32_t elem_size, int32
   q.flags &= ~DGPMP2_FLAG_Q_FULL;
   int rc = check_params(&q, nullptr);
   if (rc != DGPMP2_OK) return rc;
-  LaunchShape s{0, 0, 0, 0};
+  LaunchShape s{0, 0, 0, 0, 0, 0, 0};
   const int B = p->B > 0 ? p->B : 1;
   if (p->dof == 2) rc = (elem_size == 4) ? choose_shape<4, float>(B, p->T, false, s) : choose_shape<4, double>(B, p->T, false, s);
   else rc = (elem_size == 4) ? choose_shape<6, float>(B, p->T, false, s) : choose_shape<6, double>(B, p->T, false, s);

@@ -26,6 +26,13 @@ struct KParams {
   double r_sphere, ks, kg, reg, kd, kv, vx_lim, vy_lim;
   double qc_const[9], qc_fix[9];
   double w_const, w_fix, eps_const;
+  // Host-precomputed GP blocks for the static case (no per-(b,t) Qc^-1, not Q_FULL): row-major d x d.
+  int static_gp;        // 1: use Qs / PQs / PQPs below instead of building them per state
+  int ext_same;         // 1: err_ext == err (static weights equal to the constructor-time ones)
+  double Qs[36];        // Q^-1 from qc_const
+  double PQs[36];       // Phi^T Q^-1
+  double PQPs[36];      // Phi^T Q^-1 Phi
+  double Qf[36];        // Q^-1 from qc_fix (err_ext)
 };
 
 template <typename IO>
@@ -224,7 +231,63 @@ __device__ __forceinline__ void assemble_node(const KParams& P, const KWeights<I
     o.err += 0.5 * P.kg * s2; o.err_ext += 0.5 * P.kg * s2; o.e_sg += 0.5 * s2;
   }
 
-  // ---- GP factor t (between t and t+1): H1 = Phi on state t, H2 = -I on state t+1 ----
+  // ---- GP factors t (between t and t+1; H1 = Phi on this state) and t-1 (H2 = -I on this state) ----
+  if (P.static_gp) {
+    // constant blocks precomputed on the host; only r and the errors depend on the trajectory
+    if (t < T - 1) {
+      double g[D], Qg[D];
+      gp_residual<DOF>(th, thn, P.dt, g);
+      double gQg = 0.0, g2 = 0.0;
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        double q = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          q += P.Qs[a * D + c] * g[c];
+          o.Um[a][c] = -P.PQs[a * D + c];
+          o.Dm[a][c] += P.PQPs[a * D + c];
+        }
+        Qg[a] = q;
+        gQg += g[a] * q;
+        g2 += g[a] * g[a];
+      }
+      // r += Phi^T (Q g): rows a < DOF: Qg[a]; rows a >= DOF: dt*Qg[a-DOF] + Qg[a]
+#pragma unroll
+      for (int a = 0; a < DOF; ++a) {
+        o.r[a] += Qg[a];
+        o.r[a + DOF] += P.dt * Qg[a] + Qg[a + DOF];
+      }
+      o.err += 0.5 * gQg;
+      if (P.ext_same) {
+        o.err_ext += 0.5 * gQg;
+      } else {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          double q = 0.0;
+#pragma unroll
+          for (int c = 0; c < D; ++c) q += P.Qf[a * D + c] * g[c];
+          s += g[a] * q;
+        }
+        o.err_ext += 0.5 * s;
+      }
+      o.e_gp = 0.5 * g2;
+    }
+    if (t > 0) {
+      double g[D];
+      gp_residual<DOF>(thp, th, P.dt, g);
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        double q = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          q += P.Qs[a * D + c] * g[c];
+          o.Dm[a][c] += P.Qs[a * D + c];
+        }
+        o.r[a] -= q;
+      }
+    }
+  } else {
   if (t < T - 1) {
     double Q[D][D], g[D];
     load_qinv<DOF, IO>(P, Wt, b, t, Q);
@@ -263,7 +326,6 @@ __device__ __forceinline__ void assemble_node(const KParams& P, const KWeights<I
     for (int a = 0; a < D; ++a) g2 += g[a] * g[a];
     o.e_gp = 0.5 * g2;
   }
-  // ---- GP factor t-1 (between t-1 and t): this state carries H2 = -I ----
   if (t > 0) {
     double Q[D][D], g[D];
     load_qinv<DOF, IO>(P, Wt, b, t - 1, Q);
@@ -278,6 +340,7 @@ __device__ __forceinline__ void assemble_node(const KParams& P, const KWeights<I
       }
       o.r[a] -= ra;
     }
+  }
   }
 
   // ---- obstacle factor (obstacle_factor.py:35-40; one sphere centred at (x, y), J_fk = [I2 0]) ----

@@ -14,30 +14,40 @@
 
 namespace dgpmp2 {
 
-// Shared-memory carve-up of the step / solve kernels.
-template <int D, typename IO>
+// Launch-shape constants of the step / solve kernels for NN node slots and LPN lanes per BCR item.
+template <int D, int NN, int LPN>
+struct StepShape {
+  static constexpr int kCap = (D == 4) ? 512 : 384;                       // threads per CTA upper bound
+  static constexpr int kMaxThreads = (LPN * NN / 2 < kCap) ? ((LPN * NN / 2 + 31) / 32 * 32) : kCap;
+  // CTAs per SM that shared memory allows (band = kDoublesPerNode doubles per slot); the register
+  // budget is capped so that registers never limit residency below that.
+  static constexpr int kSmemPerCta = (Band<D, NN>::kDoublesPerNode + 3) * NN * 8 + NN * D * 8 + 1024;
+  static constexpr int kMinBlocks = (232448 / kSmemPerCta) < 1 ? 1 : ((232448 / kSmemPerCta) > 8 ? 8 : (232448 / kSmemPerCta));
+};
+
+// Shared-memory carve-up of the step / solve kernels (NN node slots, compile time).
+template <int D, int NN, typename IO>
 struct StepSmem {
-  BcrSmem<D> band;
-  double* errp;     // [2][NN] per-node error partials (err, err_ext)
+  Band<D, NN> band;
+  double* errp;     // [2][NN] per-node error partials (err, err_ext), slot order
   double* nrm;      // [NN]    per-node |dth|^2 (solve kernel only)
   IO* th;           // [NN][D] staged trajectory, natural (problem, t, a) order
   int* lvl_off;     // [kMaxLevels + 2]
-  int* fail;        // [NP]
-  int* flags;       // [NP]  solve kernel: converged flag per problem ; [NP] iteration count follows
-  __host__ __device__ static size_t bytes(int NP, int T, bool solve) {
-    const size_t NN = (size_t)NP * T;
-    size_t b = (size_t)BcrSmem<D>::kDoublesPerNode * NN * 8 + 2 * NN * 8;
-    if (solve) b += NN * 8;
-    b += NN * D * sizeof(IO);
+  int* fail;        // [NPmax]
+  int* flags;       // [2*NPmax] solve kernel: converged flag per problem, then iteration count
+  static constexpr int kMaxNP = NN / 2;
+  __host__ __device__ static constexpr size_t bytes(bool solve) {
+    size_t b = (size_t)Band<D, NN>::kDoublesPerNode * NN * 8 + 2 * (size_t)NN * 8;
+    if (solve) b += (size_t)NN * 8;
+    b += (size_t)NN * D * sizeof(IO);
     b = (b + 7) & ~(size_t)7;
-    b += (kMaxLevels + 2) * 4 + (size_t)NP * 4 * 3 + 16;
+    b += (kMaxLevels + 2) * 4 + (size_t)kMaxNP * 4 * 3 + 16;
     return b;
   }
-  __device__ __forceinline__ void carve(unsigned char* raw, int NP, int T, bool solve) {
-    const int NN = NP * T;
+  __device__ __forceinline__ void carve(unsigned char* raw, bool solve) {
     double* base = reinterpret_cast<double*>(raw);
-    band.carve(base, NN);
-    errp = base + (size_t)BcrSmem<D>::kDoublesPerNode * NN;
+    band.base = base;
+    errp = base + (size_t)Band<D, NN>::kDoublesPerNode * NN;
     double* nxt = errp + 2 * (size_t)NN;
     nrm = nxt;
     if (solve) nxt += NN;
@@ -45,44 +55,59 @@ struct StepSmem {
     size_t off = (reinterpret_cast<unsigned char*>(th + (size_t)NN * D) - raw + 7) & ~(size_t)7;
     lvl_off = reinterpret_cast<int*>(raw + off);
     fail = lvl_off + (kMaxLevels + 2);
-    flags = fail + NP;
+    flags = fail + kMaxNP;
   }
 };
 
-// Assemble all nodes of the CTA's problems from the staged trajectory into the band.
-template <int DOF, typename IO>
-__device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO>& Wt, const StepSmem<2 * DOF, IO>& S,
-                                             int b0, int np, int nlev,
+// Thread geometry shared by the step and solve kernels: each problem of the CTA owns TPP
+// consecutive threads; thread u of problem p handles node slot u during assembly (u < T) and is
+// lane (u % LPN) of BCR work item (u / LPN).
+struct CtaGeom { int p, u; bool active; };
+__device__ __forceinline__ CtaGeom cta_geom(int TPP, int np) {
+  CtaGeom g;
+  g.p = threadIdx.x / TPP;
+  g.u = threadIdx.x - g.p * TPP;
+  g.active = g.p < np;
+  return g;
+}
+
+// Assemble this thread's nodes (slots u, u + TPP, ... of problem p) from the staged trajectory into the band.
+template <int DOF, int NN, typename IO>
+__device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO>& Wt, const StepSmem<2 * DOF, NN, IO>& S,
+                                             int b0, const CtaGeom& g, int TPP, int nlev,
                                              const IO* __restrict__ start, const IO* __restrict__ goal,
                                              const IO* __restrict__ sdf) {
   constexpr int D = 2 * DOF;
-  const int T = P.T, NN = S.band.NN;
-  for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
-    const int p = m / T, slot = m - p * T;
-    const int t = bcr_state_of_slot(S.lvl_off, nlev, T, slot);
-    const int b = b0 + p;
-    double thp[D], thc[D], thn[D];
-    const IO* tp = S.th + ((size_t)p * T + t) * D;
+  const int T = P.T;
+  if (!g.active) return;
+  for (int slot = g.u; slot < T; slot += TPP) {
+  const int t = bcr_state_of_slot(S.lvl_off, nlev, T, slot);
+  const int b = b0 + g.p;
+  double thp[D], thc[D], thn[D];
+  const IO* tp = S.th + ((size_t)g.p * T + t) * D;
 #pragma unroll
-    for (int a = 0; a < D; ++a) {
-      thc[a] = (double)tp[a];
-      thp[a] = (t > 0) ? (double)tp[a - D] : 0.0;
-      thn[a] = (t < T - 1) ? (double)tp[a + D] : 0.0;
-    }
-    NodeOut<DOF> o;
-    assemble_node<DOF, IO>(P, Wt, b, t, thp, thc, thn, start + (size_t)b * D, goal + (size_t)b * D,
-                           sdf + (size_t)b * P.sdf_sb, o);
-    const int n = p * T + slot;
+  for (int a = 0; a < D; ++a) {
+    thc[a] = (double)tp[a];
+    thp[a] = (t > 0) ? (double)tp[a - D] : 0.0;
+    thn[a] = (t < T - 1) ? (double)tp[a + D] : 0.0;
+  }
+  NodeOut<DOF> o;
+  assemble_node<DOF, IO>(P, Wt, b, t, thp, thc, thn, start + (size_t)b * D, goal + (size_t)b * D,
+                         sdf + (size_t)b * P.sdf_sb, o);
+  const int n = g.p * T + slot;
+  double* dp = S.band.Dp(n);
+  double* up = S.band.Up(n);
+  double* rp = S.band.Rp(n);
 #pragma unroll
-    for (int a = 0; a < D; ++a) {
+  for (int a = 0; a < D; ++a) {
 #pragma unroll
-      for (int c = 0; c <= a; ++c) S.band.Dm[tri(a, c) * NN + n] = o.Dm[a][c];
+    for (int c = 0; c <= a; ++c) dp[tri(a, c) * NN] = o.Dm[a][c];
 #pragma unroll
-      for (int c = 0; c < D; ++c) S.band.Um[(a * D + c) * NN + n] = o.Um[a][c];
-      S.band.Rm[a * NN + n] = o.r[a];
-    }
-    S.errp[n] = o.err;
-    S.errp[NN + n] = o.err_ext;
+    for (int c = 0; c < D; ++c) up[(a * D + c) * NN] = o.Um[a][c];
+    rp[a * NN] = o.r[a];
+  }
+  S.errp[n] = o.err;
+  S.errp[NN + n] = o.err_ext;
   }
 }
 
@@ -100,39 +125,46 @@ __device__ __forceinline__ void reduce_per_problem(const double* vals, int np, i
   }
 }
 
-template <int DOF, typename IO>
-__global__ void __launch_bounds__(DOF == 2 ? 512 : 256)
-gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th, const IO* __restrict__ start,
-               const IO* __restrict__ goal, const IO* __restrict__ sdf, IO* __restrict__ dth,
-               IO* __restrict__ err, IO* __restrict__ err_ext, int* __restrict__ status, const int NP) {
-  constexpr int D = 2 * DOF;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  StepSmem<D, IO> S;
-  const int T = P.T;
-  S.carve(smem_raw, NP, T, false);
-  const int b0 = blockIdx.x * NP;
-  const int np = min(NP, P.B - b0);
-  const int NN = NP * T;
-
+template <int D, int NN, typename IO>
+__device__ __forceinline__ void cta_prologue(const StepSmem<D, NN, IO>& S, int T, int NP, int np,
+                                             const IO* __restrict__ th_src, bool solve) {
   if (threadIdx.x == 0) {
     BcrLevels lv;
     bcr_make_levels(T, lv);
     for (int l = 0; l <= lv.nlev + 1; ++l) S.lvl_off[l] = lv.off[l];
     S.lvl_off[kMaxLevels + 1] = lv.nlev;
   }
-  for (int p = threadIdx.x; p < NP; p += blockDim.x) S.fail[p] = 0;
-  {  // stage the trajectories of this CTA's problems (contiguous in HBM -> coalesced)
-    const IO* src = th + (size_t)b0 * T * D;
-    const int n = np * T * D;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) S.th[i] = __ldg(src + i);
+  for (int p = threadIdx.x; p < NP; p += blockDim.x) {
+    S.fail[p] = 0;
+    if (solve) { S.flags[p] = 0; S.flags[NP + p] = 0; }
   }
+  const int n = np * T * D;   // contiguous in HBM -> coalesced
+  for (int i = threadIdx.x; i < n; i += blockDim.x) S.th[i] = __ldg(th_src + i);
+}
+
+// One fused Gauss-Newton iteration.  grid = ceil(B / NP), block = NP * TPP threads (rounded to a warp).
+template <int DOF, int NN, int LPN, typename IO>
+__global__ void __launch_bounds__((StepShape<2 * DOF, NN, LPN>::kMaxThreads), (StepShape<2 * DOF, NN, LPN>::kMinBlocks))
+gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th, const IO* __restrict__ start,
+               const IO* __restrict__ goal, const IO* __restrict__ sdf, IO* __restrict__ dth,
+               IO* __restrict__ err, IO* __restrict__ err_ext, int* __restrict__ status, const int NP, const int TPP) {
+  constexpr int D = 2 * DOF;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  StepSmem<D, NN, IO> S;
+  const int T = P.T;
+  S.carve(smem_raw, false);
+  const int b0 = blockIdx.x * NP;
+  const int np = min(NP, P.B - b0);
+  const CtaGeom g = cta_geom(TPP, np);
+
+  cta_prologue<D, NN, IO>(S, T, NP, np, th + (size_t)b0 * T * D, false);
   __syncthreads();
   const int nlev = S.lvl_off[kMaxLevels + 1];
 
-  assemble_cta<DOF, IO>(P, Wt, S, b0, np, nlev, start, goal, sdf);
+  assemble_cta<DOF, NN, IO>(P, Wt, S, b0, g, TPP, nlev, start, goal, sdf);
   __syncthreads();
 
-  bcr_solve<D>(S.band, S.lvl_off, nlev, np, T, S.fail);   // ends with __syncthreads()
+  bcr_solve<D, NN, LPN>(S.band, S.lvl_off, nlev, T, g.active, g.p, g.u, TPP / LPN, S.fail);   // ends with a barrier
 
   {  // dth, natural order -> coalesced stores
     IO* dst = dth + (size_t)b0 * T * D;
@@ -140,7 +172,7 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int a = i % D, pt = i / D;
       const int p = pt / T, t = pt - p * T;
-      dst[i] = (IO)S.band.Rm[a * NN + p * T + bcr_slot(S.lvl_off, T, t)];
+      dst[i] = (IO)S.band.Rp(p * T + bcr_slot(S.lvl_off, T, t))[a * NN];
     }
   }
   const double invM = 1.0 / (double)P.M;
@@ -153,42 +185,32 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
 // ---------------------------------------------------------------------------
 // Persistent solve-to-convergence (DiffGPMP2Planner.forward, diff_gpmp2_planner.py:104-165)
 // ---------------------------------------------------------------------------
-template <int DOF, typename IO>
-__global__ void __launch_bounds__(DOF == 2 ? 512 : 256)
+template <int DOF, int NN, int LPN, typename IO>
+__global__ void __launch_bounds__((StepShape<2 * DOF, NN, LPN>::kMaxThreads), (StepShape<2 * DOF, NN, LPN>::kMinBlocks))
 gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th_init, const IO* __restrict__ start,
                 const IO* __restrict__ goal, const IO* __restrict__ sdf, const int max_iters, const double tol_delta,
                 IO* __restrict__ th_final, int* __restrict__ iters, IO* __restrict__ err_pi, IO* __restrict__ err_ext_pi,
-                IO* __restrict__ err_final, IO* __restrict__ err_ext_final, int* __restrict__ status, const int NP) {
+                IO* __restrict__ err_final, IO* __restrict__ err_ext_final, int* __restrict__ status, const int NP,
+                const int TPP) {
   constexpr int D = 2 * DOF;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  StepSmem<D, IO> S;
+  StepSmem<D, NN, IO> S;
   const int T = P.T;
-  S.carve(smem_raw, NP, T, true);
+  S.carve(smem_raw, true);
   int* done = S.flags;          // [NP]
   int* nit = S.flags + NP;      // [NP]
   const int b0 = blockIdx.x * NP;
   const int np = min(NP, P.B - b0);
-  const int NN = NP * T;
+  const CtaGeom g = cta_geom(TPP, np);
 
-  if (threadIdx.x == 0) {
-    BcrLevels lv;
-    bcr_make_levels(T, lv);
-    for (int l = 0; l <= lv.nlev + 1; ++l) S.lvl_off[l] = lv.off[l];
-    S.lvl_off[kMaxLevels + 1] = lv.nlev;
-  }
-  for (int p = threadIdx.x; p < NP; p += blockDim.x) { S.fail[p] = 0; done[p] = 0; nit[p] = 0; }
-  {
-    const IO* src = th_init + (size_t)b0 * T * D;
-    const int n = np * T * D;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) S.th[i] = __ldg(src + i);
-  }
+  cta_prologue<D, NN, IO>(S, T, NP, np, th_init + (size_t)b0 * T * D, true);
   __syncthreads();
   const int nlev = S.lvl_off[kMaxLevels + 1];
   const double invM = 1.0 / (double)P.M;
 
   for (int j = 0;; ++j) {
-    // assemble at the current iterate; errors at iterate j are a by-product
-    assemble_cta<DOF, IO>(P, Wt, S, b0, np, nlev, start, goal, sdf);
+    // assemble at the current iterate; the errors at iterate j are a by-product
+    assemble_cta<DOF, NN, IO>(P, Wt, S, b0, g, TPP, nlev, start, goal, sdf);
     __syncthreads();
     const bool last = (j >= max_iters);
     reduce_per_problem(S.errp, np, T, [&](int p, double s) {
@@ -208,9 +230,9 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
     for (int p = 0; p < np; ++p) all_done = all_done && (done[p] == 2);
     if (all_done || last) break;
 
-    bcr_solve<D>(S.band, S.lvl_off, nlev, np, T, S.fail);
+    bcr_solve<D, NN, LPN>(S.band, S.lvl_off, nlev, T, g.active, g.p, g.u, TPP / LPN, S.fail);
 
-    // th <- th + dth for problems still running; |dth|^2 partials (slot order, like errp)
+    // th <- th + dth for problems still running; |dth|^2 partials
     for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
       const int p = m / T, t = m - p * T;
       const int n = p * T + bcr_slot(S.lvl_off, T, t);
@@ -218,7 +240,7 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
       if (!done[p]) {
 #pragma unroll
         for (int a = 0; a < D; ++a) {
-          const double dx = S.band.Rm[a * NN + n];
+          const double dx = S.band.Rp(n)[a * NN];
           // the reference adds dtheta (I/O dtype) to th (I/O dtype): round dth first, then add
           const IO dxi = (IO)dx;
           s2 += (double)dxi * (double)dxi;

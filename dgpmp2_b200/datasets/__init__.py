@@ -1,0 +1,2 @@
+from .planning_dataset import PlanningDataset
+from .synthetic import make_problems

@@ -1,0 +1,1 @@
+from .env_2d import Env2D

@@ -1,0 +1,178 @@
+"""The planner module (API mirror of reference ``diff_gpmp2/gpmp2/diff_gpmp2_planner.py:15-299``).
+
+``DiffGPMP2Planner(gp_params, obs_params, planner_params, optim_params, env_params, robot_model,
+learn_params=None, batch_size=1, use_cuda=False)``
+  ``.step(th_currb, startb, goalb, imb, sdfb, ...)`` -> 7-tuple (:176-211): one fused CUDA launch.
+  ``.forward(th_initb, startb, goalb, imb, sdfb)``   -> 8-tuple (:92-174): the reference optimises
+      the problems one after the other with B=1 sub-calls; here the whole batch is optimised to
+      per-problem convergence in ONE persistent CUDA launch (dgpmp2_gn_solve_*), with identical
+      per-problem semantics (independent problems, same stopping rule).
+The learned-covariance networks (reference learning/*, cuDNN model code) are outside this
+package; ``get_covariances`` (the mapping from network outputs to covariances, :247-290) is kept.
+"""
+import time
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .._dev import as_float, back, to_cuda, work_dtype
+from ..utils import mat_utils
+from .plan_layer import PlanLayer
+
+
+class DiffGPMP2Planner(nn.Module):
+    def __init__(self, gp_params, obs_params, planner_params, optim_params, env_params, robot_model,
+                 learn_params=None, batch_size=1, use_cuda=False):
+        super(DiffGPMP2Planner, self).__init__()
+        self.use_cuda = torch.cuda.is_available() if use_cuda else False
+        self.device = torch.device('cuda') if self.use_cuda else torch.device('cpu')
+        self.dof = int(planner_params['dof'])
+        self.state_dim = int(planner_params['state_dim'])
+        self.total_time_sec = planner_params['total_time_sec']
+        self.total_time_step = int(planner_params['total_time_step'])
+        self.num_traj_states = self.total_time_step + 1
+        self.num_gp_factors = self.num_traj_states - 1
+        self.num_obs_factors = self.num_traj_states
+        self.optim_params, self.gp_params, self.obs_params = optim_params, gp_params, obs_params
+        self.robot_model, self.env_params, self.learn_params = robot_model, env_params, learn_params
+        self.model_type = 'feed_forward'
+        self.non_holonomic = bool(planner_params.get('non_holonomic', False))
+        self.use_vel_limits = bool(planner_params.get('use_vel_limits', False))
+        self.batch_size = batch_size
+        self.learn_module_conv = None
+        self.learn_module_fcn = None
+        if learn_params is not None:
+            raise NotImplementedError(
+                'learned-covariance networks (reference diff_gpmp2/learning) are outside the GN hot path this package '
+                'implements; predict the covariances with your own module, map them with get_covariances() and call '
+                'planner.plan_layer(th, start, goal, im, sdf, qc_inv, obscov_inv, eps) directly')
+        nl = robot_model.nlinks
+        qc_inv = torch.as_tensor(gp_params['Q_c_inv'])
+        inv_cov = mat_utils.isotropic_matrix(1.0 / torch.pow(torch.as_tensor(obs_params['cost_sigma']), 2.0), nl)
+        # constant per-trajectory covariances, same shapes as the reference (:41-48)
+        self.qc_inv_traj = torch.zeros(self.num_gp_factors, self.dof, self.dof) + qc_inv
+        self.obscov_inv_traj = torch.zeros(self.num_traj_states, nl, 1) + inv_cov
+        self.eps_traj = torch.zeros(self.num_traj_states, nl, 1) + torch.as_tensor(obs_params['epsilon_dist'])
+        self.plan_layer = PlanLayer(gp_params, obs_params, planner_params, optim_params, env_params, robot_model,
+                                    learn_params, batch_size, self.use_cuda)
+
+    # ------------------------------------------------------------------ optimise to convergence
+    def forward(self, th_initb, startb, goalb, imb, sdfb, hiddenb=None):
+        """-> (th_finalb (B,T,d), hidden, err_initb[B], err_finalb[B], err_per_iterb[B][j],
+        err_ext_per_iterb[B][j], jb[B], timeb[B])."""
+        start_t = time.time()
+        B = th_initb.shape[0]
+        plan_time = float(self.optim_params.get('plan_time', 'inf'))
+        max_iters = int(self.optim_params['max_iters'])
+        tol_delta = as_float(self.optim_params['tol_delta'])
+        pl = self.plan_layer
+        qc, w, eps = pl.static_weights(B, th_initb)
+        # keep the reference's post-conditions: the factor state of the last plan_layer call is installed
+        pl.start_prior.set_mean(startb)
+        pl.goal_prior.set_mean(goalb)
+        pl.gp_prior.Q_c_inv, pl.gp_prior.Q_inv = qc, None
+        pl.obs_factor.set_inv_cov(w)
+        pl.obs_factor.set_eps(eps)
+        pl._state = dict(start=startb, goal=goalb, qc=qc, w=w, eps=eps, static=True)
+        if plan_time != float('inf'):
+            return self._forward_timed(th_initb, startb, goalb, imb, sdfb, plan_time, start_t)
+        dt = work_dtype(th_initb, sdfb)
+        out = ops.gn_solve(pl.cparams(), to_cuda(th_initb, dt), to_cuda(startb, dt), to_cuda(goalb, dt),
+                           to_cuda(sdfb, dt), max_iters, tol_delta)
+        th_final, iters, epi, eepi, ef, eef, status = out
+        pl._check(status)
+        iters_h = iters.cpu().tolist()                   # one host sync for the whole batch
+        epi_h, eepi_h, ef_h = epi.double().cpu(), eepi.double().cpu(), ef.double().cpu().tolist()
+        err_per_iterb = [epi_h[i, :iters_h[i]].tolist() for i in range(B)]
+        err_ext_per_iterb = [eepi_h[i, :iters_h[i]].tolist() for i in range(B)]
+        err_initb = [e[0] for e in err_per_iterb]
+        elapsed = time.time() - start_t
+        return (back(th_final, th_initb).to(th_initb.dtype), None, err_initb, ef_h, err_per_iterb, err_ext_per_iterb,
+                iters_h, [elapsed] * B)
+
+    def _forward_timed(self, th_initb, startb, goalb, imb, sdfb, plan_time, start_t):
+        """Wall-clock-budgeted variant (optim_params['plan_time'] finite): batched step() loop with
+        per-problem convergence masks and the reference's budget check (:154-156)."""
+        B = th_initb.shape[0]
+        max_iters = int(self.optim_params['max_iters'])
+        tol_delta = as_float(self.optim_params['tol_delta'])
+        th = th_initb.detach().clone()
+        done = torch.zeros(B, dtype=torch.bool, device=th.device)
+        iters = [0] * B
+        epi = [[] for _ in range(B)]
+        eepi = [[] for _ in range(B)]
+        for j in range(max_iters):
+            dth, _, err, err_ext, _, _, _ = self.step(th, startb, goalb, imb, sdfb)
+            nrm = torch.norm(dth.reshape(B, -1), dim=1)
+            e_h, ee_h, nrm_h, done_h = err.reshape(-1).tolist(), err_ext.reshape(-1).tolist(), nrm.tolist(), done.tolist()
+            for i in range(B):
+                if not done_h[i]:
+                    epi[i].append(e_h[i])
+                    eepi[i].append(ee_h[i])
+                    iters[i] = j + 1
+            th = torch.where(done.reshape(B, 1, 1), th, th + dth)
+            done = done | (nrm < tol_delta)
+            if bool(done.all()):
+                break
+            if time.time() - start_t > plan_time:
+                print('Plan time over')
+                break
+        ef = self.plan_layer.error_batch(th, sdfb).reshape(-1).tolist()
+        return (th, None, [e[0] for e in epi], ef, epi, eepi, iters, [time.time() - start_t] * B)
+
+    # ------------------------------------------------------------------ one iteration
+    def step(self, th_currb, startb, goalb, imb, sdfb, conv_out=None, dtheta_currb=None, hiddenb=None):
+        """One batched GN iteration -> (dthetab, hidden, err_oldb, err_ext_oldb, qc_inv, obscov_inv, eps)."""
+        B = th_currb.shape[0]
+        qc, w, eps = self.plan_layer.static_weights(B, th_currb)
+        dthetab, err_oldb, err_ext_oldb = self.plan_layer(th_currb, startb, goalb, imb, sdfb, qc, w, eps)
+        return dthetab, None, err_oldb, err_ext_oldb, qc, w, eps
+
+    # ------------------------------------------------------------------ errors
+    def error_batch(self, thb, sdfb):
+        return self.plan_layer.error_batch(thb, sdfb)
+
+    def error_ext_batch(self, thb, sdfb):
+        return self.plan_layer.error_ext_batch(thb, sdfb)
+
+    def unweighted_errors_batch(self, thb, sdfb):
+        return self.plan_layer.unweighted_errors(thb, sdfb)
+
+    # ------------------------------------------------------------------ network output -> covariances
+    def get_covariances(self, out, mode='diag_identity', learn_eps=False):
+        """Map a learned module's output vector ``out`` (B,1,out_dim) to (qc_inv_traj, obscov_inv_traj[, eps_traj])
+        exactly as the reference does (:247-290): every quantity is an outer product q q^T of a slice of
+        ``out`` (so it is PSD), multiplied by I in 'diag_identity' mode."""
+        nl = self.robot_model.nlinks
+        G, S, B = self.num_gp_factors, self.num_obs_factors, out.shape[0]
+        n_obs = S * nl
+        if mode == 'fix_dynamics':
+            n_gp, blk = 0, 0
+        elif mode == 'diag_identity':
+            n_gp, blk = G, 1
+        elif mode == 'qc_full':
+            n_gp, blk = G * self.dof, self.dof
+        elif mode == 'q_full':
+            n_gp, blk = G * self.state_dim, self.state_dim
+        else:
+            raise NotImplementedError(mode)
+        qc_inv_traj = None
+        if blk:
+            q = out[:, 0, 0:n_gp].reshape(B, G, blk, 1)
+            qc_inv_traj = q * q.transpose(2, 3)
+            if mode == 'diag_identity':
+                qc_inv_traj = qc_inv_traj * torch.eye(self.dof, device=out.device, dtype=out.dtype)
+        o = out[:, 0, n_gp:n_gp + n_obs].reshape(B, S, nl, 1)
+        obscov_inv_traj = o * o.transpose(2, 3)
+        res = [] if mode == 'fix_dynamics' else [qc_inv_traj]
+        res.append(obscov_inv_traj)
+        if learn_eps:
+            e = out[:, 0, n_gp + n_obs:].reshape(B, S, nl, 1)
+            res.append(e * e.transpose(2, 3))
+        return res[0] if len(res) == 1 else tuple(res)
+
+    def get_obs_covariance(self, out):
+        nl = self.robot_model.nlinks
+        return torch.eye(nl, device=out.device, dtype=out.dtype).expand(self.num_obs_factors, nl, nl) * \
+            (out * out).reshape(self.num_obs_factors, 1, 1)

@@ -1,0 +1,33 @@
+"""Hinge-loss obstacle cost (API mirror of reference ``gpmp2/obstacle/obstacle_cost.py:7-38``).
+
+The SDF lookup runs in the CUDA library (dgpmp2_sdf_lookup_*); the hinge is two elementwise
+selects on its outputs.  Inside the GN step lookup + hinge + Jacobian are fused in one kernel.
+"""
+import torch
+
+from ... import ops
+from ..._dev import back, to_cuda, work_dtype
+
+
+class HingeLossObstacleCost(object):
+    def __init__(self, env_params, batch_size=1, use_cuda=False):
+        self.use_cuda = torch.cuda.is_available() if use_cuda else False
+        self.device = torch.device('cuda') if self.use_cuda else torch.device('cpu')
+        self.env_params = env_params
+
+    def hinge_loss_signed_batch(self, sphere_centersb, r_vec, epsb, sdfb):
+        """sphere_centersb (B,T,nlinks,2), epsb (B,T,nlinks,1)-like, sdfb (B,1,H,W)
+        -> cost (B,T,nlinks,1), H (B,T,nlinks,2)."""
+        B, T, nl, _ = sphere_centersb.shape
+        dt = work_dtype(sphere_centersb, sdfb)
+        x_lims, y_lims = self.env_params['x_lims'], self.env_params['y_lims']
+        res = (x_lims[1] - x_lims[0]) / (sdfb.shape[-1])
+        pts = to_cuda(sphere_centersb, dt).reshape(B, T * nl, 2)
+        dist, J = ops.sdf_lookup(to_cuda(sdfb, dt), pts, res, x_lims[0], y_lims[0])
+        eps_tot = (torch.as_tensor(epsb).to(dist.device, dt) + float(torch.as_tensor(r_vec).reshape(-1)[0])).reshape(-1, T * nl, 1)
+        active = dist <= eps_tot
+        cost = torch.where(active, eps_tot - dist, torch.zeros_like(dist))
+        H = torch.where(active, -1.0 * J, torch.zeros_like(J))
+        out_dt = sphere_centersb.dtype
+        return (back(cost, sphere_centersb).to(out_dt).reshape(B, T, nl, 1),
+                back(H, sphere_centersb).to(out_dt).reshape(B, T, nl, 2))

@@ -1,0 +1,198 @@
+"""One batched Gauss-Newton step as a torch module (API mirror of reference
+``diff_gpmp2/gpmp2/plan_layer.py:13-99``).
+
+Same constructor, same ``forward(thb, startb, goalb, imb, sdfb, qc_inv_trajb, obscov_inv_trajb,
+eps_trajb) -> (dthetab, err, err_ext)``, same factor attributes (``start_prior``, ``goal_prior``,
+``gp_prior``, ``obs_factor``, ``gp_prior_fix``, ``obs_factor_fix``, ``dyn_factor``, ``vel_factor``)
+and the same statefulness: ``forward`` installs the per-call means / covariances / eps on the
+factor objects and ``error_batch`` / ``error_ext_batch`` evaluate against what was last installed.
+
+What differs is everything underneath: the reference builds dense A (B,M,N), b, K with
+masked_scatter_ and solves dense normal equations (:152-234); here one fused CUDA kernel
+(dgpmp2_gn_step_*) evaluates the factors, keeps the block-tridiagonal band in shared memory,
+solves it by block cyclic reduction and returns dtheta and both errors.  ``batch_size`` is
+accepted for compatibility but any batch size works.  There is no CPU path: CPU tensors are
+staged to the GPU and the results handed back on the caller's device.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+from .._dev import as_float, back, to_cuda, work_dtype
+from .custom_factors import NonHolonomicFactor, VelocityLimitFactor
+from .gp import GPFactor, PriorFactor
+from .obstacle import ObstacleFactor
+
+
+class PlanLayer(nn.Module):
+    def __init__(self, gp_params, obs_params, planner_params, optim_params, env_params, robot_model,
+                 learn_params=None, batch_size=1, use_cuda=False):
+        super(PlanLayer, self).__init__()
+        self.use_cuda = torch.cuda.is_available() if use_cuda else False
+        self.device = torch.device('cuda') if self.use_cuda else torch.device('cpu')
+        self.gp_params, self.obs_params, self.planner_params = gp_params, obs_params, planner_params
+        self.optim_params, self.env_params, self.robot_model = optim_params, env_params, robot_model
+        self.learn_params = learn_params
+        self.batch_size = batch_size
+        self.dof = int(planner_params['dof'])
+        self.state_dim = int(planner_params['state_dim'])
+        self.total_time_sec = planner_params['total_time_sec']
+        self.total_time_step = int(planner_params['total_time_step'])
+        self.num_traj_states = self.total_time_step + 1
+        self.dt = self.total_time_sec * 1.0 / self.total_time_step * 1.0
+        self.non_holonomic = bool(planner_params.get('non_holonomic', False))
+        self.use_vel_limits = bool(planner_params.get('use_vel_limits', False))
+        self.num_gp_factors = self.num_traj_states - 1
+        self.num_prior_factors = 2
+        self.num_obs_factors = self.num_traj_states
+        self.nlinks = self.robot_model.nlinks
+        if self.nlinks != 1:
+            raise NotImplementedError('the GN kernels implement one collision sphere per state (nlinks == 1)')
+        if self.state_dim != 2 * self.dof or self.dof not in (2, 3):
+            raise NotImplementedError('state_dim must be 2*dof with dof in {2, 3}')
+        self.M = self.state_dim * (self.num_gp_factors + self.num_prior_factors) + self.num_obs_factors * self.nlinks
+        if self.non_holonomic:
+            self.num_dynamics_factors = self.num_traj_states
+            self.M += self.num_dynamics_factors
+        if self.use_vel_limits:
+            self.num_vel_factors = self.num_traj_states
+            self.M += self.dof * self.num_vel_factors
+        self.N = self.state_dim * self.num_traj_states
+        self.dynamics_mode = learn_params['dgpmp2']['dynamics_mode'] if learn_params is not None else None
+        self.q_full = self.dynamics_mode == 'q_full'
+
+        # factor objects with the reference's names (they carry the per-call state)
+        T = self.num_traj_states
+        self.gp_prior = GPFactor(self.dof, self.dt, self.num_gp_factors, batch_size, self.use_cuda)
+        self.start_prior = PriorFactor(self.state_dim, gp_params['K_s'], batch_size, self.use_cuda)
+        self.goal_prior = PriorFactor(self.state_dim, gp_params['K_g'], batch_size, self.use_cuda)
+        self.obs_factor = ObstacleFactor(self.state_dim, T, obs_params['epsilon_dist'], env_params, robot_model, batch_size, self.use_cuda)
+        self.gp_prior_fix = GPFactor(self.dof, self.dt, self.num_gp_factors, batch_size, self.use_cuda)
+        self.obs_factor_fix = ObstacleFactor(self.state_dim, T, obs_params['epsilon_dist'], env_params, robot_model, batch_size, self.use_cuda)
+        if self.non_holonomic:
+            self.dyn_factor = NonHolonomicFactor(self.dof, gp_params['K_d'], T, batch_size, self.use_cuda)
+        if self.use_vel_limits:
+            self.vel_factor = VelocityLimitFactor(self.state_dim, T, gp_params['K_v'], batch_size, self.use_cuda)
+            self.vel_factor.set_v_traj(torch.as_tensor(gp_params['v_x']), torch.as_tensor(gp_params['v_y']))
+        self.qc_inv_fix = torch.as_tensor(gp_params['Q_c_inv']).detach().double().cpu()
+        self.gp_prior_fix.Q_c_inv = self.qc_inv_fix
+        self.strict = True          # raise (like torch.cholesky) when a problem's system is not positive definite
+        self.last_status = None
+        self._state = None          # weights installed by the last forward()
+        self._static_views = {}
+
+    # ------------------------------------------------------------------ parameters
+    def cparams(self, q_full=None, eps_static=None, w_static=None, qc_static=None):
+        gp, ob = self.gp_params, self.obs_params
+        return _lib.make_params(
+            B=1, T=self.num_traj_states, dof=self.dof, H=1, W=1, x_lims=self.env_params['x_lims'],
+            y_lims=self.env_params['y_lims'], total_time_sec=self.total_time_sec,
+            r_sphere=self.robot_model.get_sphere_radii(), K_s=gp['K_s'], K_g=gp['K_g'], reg=self.optim_params['reg'],
+            Q_c_inv=gp['Q_c_inv'], cost_sigma=ob['cost_sigma'], epsilon_dist=ob['epsilon_dist'],
+            non_holonomic=self.non_holonomic, K_d=gp.get('K_d'), use_vel_limits=self.use_vel_limits, K_v=gp.get('K_v'),
+            v_x=gp.get('v_x'), v_y=gp.get('v_y'), q_full=self.q_full if q_full is None else q_full,
+            Q_c_inv_static=qc_static, w_obs_static=w_static, eps_static=eps_static)
+
+    def static_weights(self, B, like):
+        """The planner's constant covariances as (B, ...) expanded views (zero-copy); passing exactly
+        these objects to ``forward`` selects the constant fast path of the kernel."""
+        key = (B, like.device, like.dtype)
+        if key not in self._static_views:
+            T, dof = self.num_traj_states, self.dof
+            qc = torch.as_tensor(self.gp_params['Q_c_inv']).to(like.device, like.dtype).reshape(1, 1, dof, dof).expand(B, T - 1, dof, dof)
+            w = torch.full((1, 1, 1, 1), 1.0 / as_float(self.obs_params['cost_sigma']) ** 2, device=like.device, dtype=like.dtype).expand(B, T, 1, 1)
+            eps = torch.full((1, 1, 1, 1), as_float(self.obs_params['epsilon_dist']), device=like.device, dtype=like.dtype).expand(B, T, 1, 1)
+            self._static_views[key] = (qc, w, eps)
+        return self._static_views[key]
+
+    def _is_static(self, qc, w, eps):
+        for views in self._static_views.values():
+            if qc is views[0] and w is views[1] and eps is views[2]:
+                return True
+        return False
+
+    # ------------------------------------------------------------------ the GN step
+    def forward(self, thb, startb, goalb, imb, sdfb, qc_inv_trajb, obscov_inv_trajb, eps_trajb):
+        """One GN iteration for the whole batch (``imb`` is accepted and ignored, as in the reference)."""
+        self.start_prior.set_mean(startb)
+        self.goal_prior.set_mean(goalb)
+        if self.q_full:
+            self.gp_prior.set_inv_cov(qc_inv_trajb)
+        else:
+            self.gp_prior.Q_c_inv, self.gp_prior.Q_inv = qc_inv_trajb, None     # Q^-1 is rebuilt inside the kernel
+        self.obs_factor.set_inv_cov(obscov_inv_trajb)
+        self.obs_factor.set_eps(eps_trajb)
+        static = self._is_static(qc_inv_trajb, obscov_inv_trajb, eps_trajb)
+        self._state = dict(start=startb, goal=goalb, qc=qc_inv_trajb, w=obscov_inv_trajb, eps=eps_trajb, static=static)
+        dt = work_dtype(thb, sdfb)
+        B = thb.shape[0]
+        th, st, go, sdf = to_cuda(thb, dt), to_cuda(startb, dt), to_cuda(goalb, dt), to_cuda(sdfb, dt)
+        p = self.cparams()
+        if static:
+            dth, err, err_ext, status = ops.gn_step(p, th, st, go, sdf, want_status=True)
+        else:
+            dth, err, err_ext, status = ops.gn_step(p, th, st, go, sdf, qc_inv=to_cuda(qc_inv_trajb, dt),
+                                                    w_obs=to_cuda(obscov_inv_trajb, dt), eps=to_cuda(eps_trajb, dt),
+                                                    want_status=True)
+        self._check(status)
+        out_dt = thb.dtype
+        return (back(dth, thb).to(out_dt), back(err, thb).to(out_dt).reshape(B, 1, 1),
+                back(err_ext, thb).to(out_dt).reshape(B, 1, 1))
+
+    def _check(self, status):
+        self.last_status = status
+        if self.strict and status is not None:
+            bad = torch.nonzero(status)
+            if bad.numel() > 0:
+                b = int(bad[0])
+                raise RuntimeError('cholesky: the Gauss-Newton system of problem %d is not positive-definite '
+                                   '(first failing state %d)' % (b, int(status[b]) - 1))
+
+    # ------------------------------------------------------------------ errors
+    def _errors(self, thb, sdfb):
+        if self._state is None:
+            raise RuntimeError('PlanLayer: call forward() (or set the factor means / covariances) before error_batch')
+        s = self._state
+        dt = work_dtype(thb, sdfb)
+        p = self.cparams()
+        kw = {}
+        if not s['static']:
+            kw = dict(qc_inv=to_cuda(s['qc'], dt), w_obs=to_cuda(s['w'], dt), eps=to_cuda(s['eps'], dt))
+        outs = ops.errors(p, to_cuda(thb, dt), to_cuda(s['start'], dt), to_cuda(s['goal'], dt), to_cuda(sdfb, dt), **kw)
+        return [back(o, thb).to(thb.dtype) for o in outs]
+
+    def error_batch(self, thb, sdfb):
+        """Normalised weighted error 0.5 sum e^T K e / M with the covariances of the last forward() -> (B,1,1)."""
+        with torch.no_grad():
+            return self._errors(thb, sdfb)[0].reshape(-1, 1, 1)
+
+    def error_ext_batch(self, thb, sdfb):
+        """Same with the constructor-time covariances (reference :310-345) -> (B,1,1)."""
+        return self._errors(thb, sdfb)[1].reshape(-1, 1, 1)
+
+    def start_goal_error(self, thb):
+        dummy = torch.zeros(thb.shape[0], 1, 2, 2, device=thb.device, dtype=thb.dtype)
+        return self._errors(thb, dummy)[2].reshape(-1, 1)
+
+    def gp_error(self, thb):
+        dummy = torch.zeros(thb.shape[0], 1, 2, 2, device=thb.device, dtype=thb.dtype)
+        return self._errors(thb, dummy)[3].reshape(-1, 1, 1)
+
+    def obs_error(self, thb, sdfb):
+        return self._errors(thb, sdfb)[4].reshape(-1, 1, 1)
+
+    def unweighted_errors(self, thb, sdfb):
+        """(err_sg (B,1), err_gp (B,1,1), err_obs (B,1,1)) from ONE factor sweep."""
+        o = self._errors(thb, sdfb)
+        return o[2].reshape(-1, 1), o[3].reshape(-1, 1, 1), o[4].reshape(-1, 1, 1)
+
+    # ------------------------------------------------------------------ the information system itself
+    def information_band(self, thb, sdfb):
+        """Block-tridiagonal normal equations of the last-installed problem in float64:
+        D (B,T,d,d), U (B,T-1,d,d), r (B,T,d) -- what the reference holds as dense A^T K A + reg I, A^T K b."""
+        s = self._state
+        dt = work_dtype(thb, sdfb)
+        kw = {}
+        if not s['static']:
+            kw = dict(qc_inv=to_cuda(s['qc'], dt), w_obs=to_cuda(s['w'], dt), eps=to_cuda(s['eps'], dt))
+        return ops.band(self.cparams(), to_cuda(thb, dt), to_cuda(s['start'], dt), to_cuda(s['goal'], dt), to_cuda(sdfb, dt), **kw)
