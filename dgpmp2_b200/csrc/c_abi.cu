@@ -4,6 +4,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "../../include/dgpmp2_b200.h"
 #include "kernels.cuh"
@@ -157,9 +160,23 @@ int choose_shape(int B, int T, bool solve, LaunchShape& s) {
   return DGPMP2_OK;
 }
 
+// Opt a kernel in to > 48 KB of dynamic shared memory, once per (kernel, device).
 template <typename K>
 int allow_smem(K kernel, int bytes) {
-  if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  if (bytes <= 48 * 1024) return DGPMP2_OK;
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  const void* key = reinterpret_cast<const void*>(kernel);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (const auto& e : done)
+      if (e.first == key && e.second == dev) return DGPMP2_OK;
+  }
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  std::lock_guard<std::mutex> lk(mu);
+  done.emplace_back(key, dev);
   return DGPMP2_OK;
 }
 

@@ -343,11 +343,18 @@ def normal_equations(A, b, K, reg: float):
 
 
 def solve_dense(A, b, K, reg: float) -> torch.Tensor:
-    """plan_layer.py:214-234: upper Cholesky + two explicit inverses."""
+    """plan_layer.py:214-234: upper Cholesky, then the two explicit N x N inverses of the triangular
+    factor applied with bmm.  The reference forms the inverses with ``torch.inverse`` (LU); here the
+    same inverses are formed with a triangular solve against the identity, because MKL's batched
+    getrf/getri path hangs on the GPU box's host CPU ("oneMKL ERROR: Parameter 6 ... DLASWP").
+    Same arithmetic structure (explicit inverse + dense bmm), same result to rounding."""
     LAM, R = normal_equations(A, b, K, reg)
     u = torch.linalg.cholesky(LAM).transpose(1, 2).contiguous()   # torch.cholesky(LAM, upper=True)
-    z = torch.bmm(torch.inverse(u.transpose(1, 2)), R)
-    dth = torch.bmm(torch.inverse(u), z)
+    eye = torch.eye(LAM.shape[-1], dtype=F64).expand_as(LAM)
+    ut_inv = torch.linalg.solve_triangular(u.transpose(1, 2), eye, upper=False)
+    u_inv = torch.linalg.solve_triangular(u, eye, upper=True)
+    z = torch.bmm(ut_inv, R)
+    dth = torch.bmm(u_inv, z)
     return dth
 
 
