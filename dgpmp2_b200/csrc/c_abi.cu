@@ -86,6 +86,10 @@ KParams make_kparams(const dgpmp2_params* p) {
     }
   k.static_gp = 0;   // set by the caller once the weights are known
   k.ext_same = 0;
+  BcrLevels lv;
+  bcr_make_levels(p->T, lv);
+  k.nlev = lv.nlev;
+  for (int l = 0; l < 18; ++l) k.lvl_off[l] = (l <= lv.nlev + 1) ? lv.off[l] : 0;
   return k;
 }
 
@@ -111,7 +115,7 @@ KWeights<IO> make_kweights(const dgpmp2_weights* w) {
   return k;
 }
 
-struct LaunchShape { int nn, lpn, np, tpp, threads, smem, grid; };
+struct LaunchShape { int np, tpp, threads, smem, grid; };
 
 int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
@@ -120,41 +124,41 @@ int env_int(const char* name, int dflt) {
   return v > 0 ? v : dflt;
 }
 
-// Node slots per CTA (compile-time NN), problems per CTA, threads per problem.
-// One problem per CTA once T >= 33 (the CTA-wide barriers of the BCR then only couple the warps
-// of one problem and the scheduler overlaps different problems' sparse and dense levels);
-// several short problems share a CTA so that it still fills a few warps.
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// Problems per CTA (NP) and CTA size.  All problems an SM has to process are put in ONE CTA when
+// they fit (NP = ceil(B / #SMs), bounded by shared memory and the thread limit): the BCR work items
+// of all of them are packed onto consecutive lanes, so the sparse deep levels of several problems
+// share warps, and one CTA per SM launches without a ramp.  Threads = kLPN lanes per level-1 item.
 template <int D, typename IO>
 int choose_shape(int B, int T, bool solve, LaunchShape& s) {
-  int nn;
-  if (T <= 64) nn = 64;
-  else if (T <= 128) nn = 128;
-  else if (T <= 256) nn = 256;
-  else if (T <= 512 && D == 4) nn = 512;
-  else return DGPMP2_ERR_UNSUPPORTED;
-  const int lpn = (env_int("DGPMP2_LPN", 4) == 2) ? 2 : 4;
-  const int cap = (D == 4) ? 512 : 384;
-  int max_threads = lpn * nn / 2;
-  max_threads = (max_threads < cap) ? ((max_threads + 31) / 32 * 32) : cap;
-  int np = nn / T;
-  if (np < 1) np = 1;
+  const int max_threads = (D == 4) ? 512 : 256;
+  const int items = (T + 1) / 2;                 // level-1 work items (and assembly needs T threads ~ 2 * items)
+  int np = (B + sm_count() - 1) / sm_count();
   np = env_int("DGPMP2_NP", np);
-  if (np > nn / T) np = nn / T;
   if (np > B) np = B;
   if (np < 1) np = 1;
-  int tpp = lpn * ((T + 1) / 2);
-  if (np * tpp > max_threads) tpp = (max_threads / np) / lpn * lpn;
-  if (tpp < lpn) return DGPMP2_ERR_UNSUPPORTED;
-  s.nn = nn; s.lpn = lpn; s.np = np; s.tpp = tpp;
-  s.threads = (np * tpp + 31) / 32 * 32;
-  size_t bytes = 0;
-  switch (nn) {
-    case 64: bytes = StepSmem<D, 64, IO>::bytes(solve); break;
-    case 128: bytes = StepSmem<D, 128, IO>::bytes(solve); break;
-    case 256: bytes = StepSmem<D, 256, IO>::bytes(solve); break;
-    default: bytes = StepSmem<D, 512, IO>::bytes(solve); break;
-  }
+  while (np > 1 && StepSmem<D, IO>::bytes(np, T, solve) > (size_t)kSmemLimit) --np;
+  const size_t bytes = StepSmem<D, IO>::bytes(np, T, solve);
   if (bytes > (size_t)kSmemLimit) return DGPMP2_ERR_UNSUPPORTED;
+  int threads = kLPN * items * np;
+  threads = (threads + 31) / 32 * 32;
+  if (threads > max_threads) threads = max_threads;
+  if (threads < 64) threads = 64;
+  threads = env_int("DGPMP2_THREADS", threads);
+  if (threads > max_threads) threads = max_threads;
+  s.np = np; s.tpp = threads / np;
+  s.threads = threads;
   s.smem = (int)bytes;
   s.grid = (B + np - 1) / np;
   return DGPMP2_OK;
@@ -180,40 +184,18 @@ int allow_smem(K kernel, int bytes) {
   return DGPMP2_OK;
 }
 
-template <int DOF, int NN, int LPN, typename IO>
-int launch_step_nn(const LaunchShape& s, const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start,
-                   const IO* goal, const IO* sdf, IO* dth, IO* err, IO* err_ext, int32_t* status, cudaStream_t st) {
-  auto kern = gn_step_kernel<DOF, NN, LPN, IO>;
-  int rc = allow_smem(kern, s.smem);
-  if (rc != DGPMP2_OK) return rc;
-  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, s.np, s.tpp);
-  CUDA_TRY(cudaGetLastError());
-  return DGPMP2_OK;
-}
-
-template <int DOF, int LPN, typename IO>
-int launch_step_lpn(const LaunchShape& s, const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start,
-                    const IO* goal, const IO* sdf, IO* dth, IO* err, IO* err_ext, int32_t* status, cudaStream_t st) {
-  switch (s.nn) {
-    case 64: return launch_step_nn<DOF, 64, LPN, IO>(s, k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
-    case 128: return launch_step_nn<DOF, 128, LPN, IO>(s, k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
-    case 256: return launch_step_nn<DOF, 256, LPN, IO>(s, k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
-    default:
-      if constexpr (DOF == 2)
-        return launch_step_nn<DOF, 512, LPN, IO>(s, k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
-      else
-        return DGPMP2_ERR_UNSUPPORTED;
-  }
-}
-
 template <int DOF, typename IO>
 int launch_step(const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start, const IO* goal, const IO* sdf,
                 IO* dth, IO* err, IO* err_ext, int32_t* status, cudaStream_t st) {
   LaunchShape s;
   int rc = choose_shape<2 * DOF, IO>(k.B, k.T, false, s);
   if (rc != DGPMP2_OK) return rc;
-  if (s.lpn == 2) return launch_step_lpn<DOF, 2, IO>(s, k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
-  return launch_step_lpn<DOF, 4, IO>(s, k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
+  auto kern = gn_step_kernel<DOF, IO>;
+  rc = allow_smem(kern, s.smem);
+  if (rc != DGPMP2_OK) return rc;
+  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, s.np);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
 }
 
 template <typename IO>
@@ -231,19 +213,6 @@ int gn_step_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO
   return launch_step<3, IO>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
 }
 
-template <int DOF, int NN, int LPN, typename IO>
-int launch_solve_nn(const LaunchShape& s, const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start,
-                    const IO* goal, const IO* sdf, int max_iters, double tol, IO* th_final, int32_t* iters, IO* epi,
-                    IO* eepi, IO* ef, IO* eef, int32_t* status, cudaStream_t st) {
-  auto kern = gn_solve_kernel<DOF, NN, LPN, IO>;
-  int rc = allow_smem(kern, s.smem);
-  if (rc != DGPMP2_OK) return rc;
-  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, max_iters, tol, th_final, iters, epi, eepi, ef,
-                                          eef, status, s.np, s.tpp);
-  CUDA_TRY(cudaGetLastError());
-  return DGPMP2_OK;
-}
-
 template <int DOF, typename IO>
 int launch_solve(const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start, const IO* goal, const IO* sdf,
                  int max_iters, double tol, IO* th_final, int32_t* iters, IO* epi, IO* eepi, IO* ef, IO* eef,
@@ -251,23 +220,13 @@ int launch_solve(const KParams& k, const KWeights<IO>& kw, const IO* th, const I
   LaunchShape s;
   int rc = choose_shape<2 * DOF, IO>(k.B, k.T, true, s);
   if (rc != DGPMP2_OK) return rc;
-#define DGPMP2_SOLVE_CASE(NNV, LPNV) \
-  return launch_solve_nn<DOF, NNV, LPNV, IO>(s, k, kw, th, start, goal, sdf, max_iters, tol, th_final, iters, epi, eepi, ef, eef, status, st)
-  if (s.lpn == 2) {
-    switch (s.nn) {
-      case 64: DGPMP2_SOLVE_CASE(64, 2);
-      case 128: DGPMP2_SOLVE_CASE(128, 2);
-      case 256: DGPMP2_SOLVE_CASE(256, 2);
-      default: if constexpr (DOF == 2) { DGPMP2_SOLVE_CASE(512, 2); } else { return DGPMP2_ERR_UNSUPPORTED; }
-    }
-  }
-  switch (s.nn) {
-    case 64: DGPMP2_SOLVE_CASE(64, 4);
-    case 128: DGPMP2_SOLVE_CASE(128, 4);
-    case 256: DGPMP2_SOLVE_CASE(256, 4);
-    default: if constexpr (DOF == 2) { DGPMP2_SOLVE_CASE(512, 4); } else { return DGPMP2_ERR_UNSUPPORTED; }
-  }
-#undef DGPMP2_SOLVE_CASE
+  auto kern = gn_solve_kernel<DOF, IO>;
+  rc = allow_smem(kern, s.smem);
+  if (rc != DGPMP2_OK) return rc;
+  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, max_iters, tol, th_final, iters, epi, eepi, ef,
+                                          eef, status, s.np);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
 }
 
 template <typename IO>
@@ -425,6 +384,12 @@ int gn_step_host_impl(const dgpmp2_params* p, const IO* th, const IO* start, con
 
 }  // namespace
 
+#ifdef DGPMP2_TIMING
+extern "C" int dgpmp2_debug_phase_clocks(long long* out) {
+  return cudaMemcpyFromSymbol(out, dgpmp2::g_phase_clock, sizeof(long long) * 64) == cudaSuccess ? 0 : -3;
+}
+#endif
+
 extern "C" {
 
 int dgpmp2_abi_version(void) { return DGPMP2_ABI_VERSION; }
@@ -533,7 +498,7 @@ int dgpmp2_gn_step_launch_shape(const dgpmp2_params* p, int32_t elem_size, int32
   q.flags &= ~DGPMP2_FLAG_Q_FULL;
   int rc = check_params(&q, nullptr);
   if (rc != DGPMP2_OK) return rc;
-  LaunchShape s{0, 0, 0, 0, 0, 0, 0};
+  LaunchShape s{0, 0, 0, 0, 0};
   const int B = p->B > 0 ? p->B : 1;
   if (p->dof == 2) rc = (elem_size == 4) ? choose_shape<4, float>(B, p->T, false, s) : choose_shape<4, double>(B, p->T, false, s);
   else rc = (elem_size == 4) ? choose_shape<6, float>(B, p->T, false, s) : choose_shape<6, double>(B, p->T, false, s);

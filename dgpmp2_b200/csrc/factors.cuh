@@ -33,6 +33,9 @@ struct KParams {
   double PQs[36];       // Phi^T Q^-1
   double PQPs[36];      // Phi^T Q^-1 Phi
   double Qf[36];        // Q^-1 from qc_fix (err_ext)
+  // BCR level table (bcr.cuh), computed on the host: lvl_off[l] = first node slot of level l
+  int nlev;
+  int lvl_off[18];
 };
 
 template <typename IO>

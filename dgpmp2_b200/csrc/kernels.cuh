@@ -10,130 +10,102 @@
 //   factors_kernel    stand-alone factor outputs (GPFactor / ObstacleFactor / custom factors).
 //   sdf_lookup_kernel bilinear_interpolate.
 #pragma once
+#ifdef DGPMP2_TIMING
+#define DGPMP2_BCR_STAMP(i) do { if (blockIdx.x == (DGPMP2_TIMING - 1) && threadIdx.x == 0) dgpmp2::g_phase_clock_fwd(i); } while (0)
+namespace dgpmp2 { __device__ void g_phase_clock_fwd(int i); }
+#endif
 #include "bcr.cuh"
 
 namespace dgpmp2 {
 
-// Launch-shape constants of the step / solve kernels for NN node slots and LPN lanes per BCR item.
-template <int D, int NN, int LPN>
-struct StepShape {
-  static constexpr int kCap = (D == 4) ? 512 : 384;                       // threads per CTA upper bound
-  static constexpr int kMaxThreads = (LPN * NN / 2 < kCap) ? ((LPN * NN / 2 + 31) / 32 * 32) : kCap;
-  // CTAs per SM that shared memory allows (band = kDoublesPerNode doubles per slot); the register
-  // budget is capped so that registers never limit residency below that.
-  static constexpr int kSmemPerCta = (Band<D, NN>::kDoublesPerNode + 3) * NN * 8 + NN * D * 8 + 1024;
-  static constexpr int kMinBlocks = (232448 / kSmemPerCta) < 1 ? 1 : ((232448 / kSmemPerCta) > 8 ? 8 : (232448 / kSmemPerCta));
-};
-
-// Shared-memory carve-up of the step / solve kernels (NN node slots, compile time).
-template <int D, int NN, typename IO>
+// Shared-memory carve-up of the step / solve kernels: NP problems x T node records (bcr.cuh),
+// the staged trajectory, per-node |dth|^2 (solve kernel), the level table and per-problem flags.
+template <int D, typename IO>
 struct StepSmem {
-  Band<D, NN> band;
-  double* errp;     // [2][NN] per-node error partials (err, err_ext), slot order
-  double* nrm;      // [NN]    per-node |dth|^2 (solve kernel only)
-  IO* th;           // [NN][D] staged trajectory, natural (problem, t, a) order
+  double* nodes;    // [NP*T] records of Node<D>::kStride doubles
+  double* nrm;      // [NP*T] per-node |dth|^2 (solve kernel only)
+  IO* th;           // [NP*T][D] staged trajectory, natural (problem, t, a) order
   int* lvl_off;     // [kMaxLevels + 2]
-  int* fail;        // [NPmax]
-  int* flags;       // [2*NPmax] solve kernel: converged flag per problem, then iteration count
-  static constexpr int kMaxNP = NN / 2;
-  __host__ __device__ static constexpr size_t bytes(bool solve) {
-    size_t b = (size_t)Band<D, NN>::kDoublesPerNode * NN * 8 + 2 * (size_t)NN * 8;
-    if (solve) b += (size_t)NN * 8;
-    b += (size_t)NN * D * sizeof(IO);
-    b = (b + 7) & ~(size_t)7;
-    b += (kMaxLevels + 2) * 4 + (size_t)kMaxNP * 4 * 3 + 16;
+  int* fail;        // [NP]
+  int* flags;       // [2*NP] solve kernel: converged flag per problem, then iteration count
+  __host__ __device__ static size_t bytes(int NP, int T, bool solve) {
+    const size_t NN = (size_t)NP * T;
+    size_t b = NN * Node<D>::kStride * 8;
+    if (solve) b += NN * 8;
+    b += NN * D * sizeof(IO);
+    b = (b + 15) & ~(size_t)15;
+    b += (kMaxLevels + 2) * 4 + (size_t)NP * 4 * 3 + 16;
     return b;
   }
-  __device__ __forceinline__ void carve(unsigned char* raw, bool solve) {
-    double* base = reinterpret_cast<double*>(raw);
-    band.base = base;
-    errp = base + (size_t)Band<D, NN>::kDoublesPerNode * NN;
-    double* nxt = errp + 2 * (size_t)NN;
+  __device__ __forceinline__ void carve(unsigned char* raw, int NP, int T, bool solve) {
+    const size_t NN = (size_t)NP * T;
+    nodes = reinterpret_cast<double*>(raw);
+    double* nxt = nodes + NN * Node<D>::kStride;
     nrm = nxt;
     if (solve) nxt += NN;
     th = reinterpret_cast<IO*>(nxt);
-    size_t off = (reinterpret_cast<unsigned char*>(th + (size_t)NN * D) - raw + 7) & ~(size_t)7;
+    size_t off = (reinterpret_cast<unsigned char*>(th + NN * D) - raw + 15) & ~(size_t)15;
     lvl_off = reinterpret_cast<int*>(raw + off);
     fail = lvl_off + (kMaxLevels + 2);
-    flags = fail + kMaxNP;
+    flags = fail + NP;
   }
 };
 
-// Thread geometry shared by the step and solve kernels: each problem of the CTA owns TPP
-// consecutive threads; thread u of problem p handles node slot u during assembly (u < T) and is
-// lane (u % LPN) of BCR work item (u / LPN).
-struct CtaGeom { int p, u; bool active; };
-__device__ __forceinline__ CtaGeom cta_geom(int TPP, int np) {
-  CtaGeom g;
-  g.p = threadIdx.x / TPP;
-  g.u = threadIdx.x - g.p * TPP;
-  g.active = g.p < np;
-  return g;
-}
-
-// Assemble this thread's nodes (slots u, u + TPP, ... of problem p) from the staged trajectory into the band.
-template <int DOF, int NN, typename IO>
-__device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO>& Wt, const StepSmem<2 * DOF, NN, IO>& S,
-                                             int b0, const CtaGeom& g, int TPP, int nlev,
+// Assemble the CTA's np * T nodes (one thread per node record, records enumerated problem-major
+// in slot order) from the staged trajectory.
+template <int DOF, typename IO>
+__device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO>& Wt, const StepSmem<2 * DOF, IO>& S,
+                                             int b0, int np, int nlev,
                                              const IO* __restrict__ start, const IO* __restrict__ goal,
                                              const IO* __restrict__ sdf) {
   constexpr int D = 2 * DOF;
+  using N = Node<D>;
   const int T = P.T;
-  if (!g.active) return;
-  for (int slot = g.u; slot < T; slot += TPP) {
-  const int t = bcr_state_of_slot(S.lvl_off, nlev, T, slot);
-  const int b = b0 + g.p;
-  double thp[D], thc[D], thn[D];
-  const IO* tp = S.th + ((size_t)g.p * T + t) * D;
+  const float inv_T = 1.0f / (float)T;
+  for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
+    const int p = fast_div(m, inv_T), slot = m - p * T;
+    const int t = bcr_state_of_slot(S.lvl_off, nlev, T, slot);
+    const int b = b0 + p;
+    double thp[D], thc[D], thn[D];
+    const IO* tp = S.th + ((size_t)p * T + t) * D;
 #pragma unroll
-  for (int a = 0; a < D; ++a) {
-    thc[a] = (double)tp[a];
-    thp[a] = (t > 0) ? (double)tp[a - D] : 0.0;
-    thn[a] = (t < T - 1) ? (double)tp[a + D] : 0.0;
-  }
-  NodeOut<DOF> o;
-  assemble_node<DOF, IO>(P, Wt, b, t, thp, thc, thn, start + (size_t)b * D, goal + (size_t)b * D,
-                         sdf + (size_t)b * P.sdf_sb, o);
-  const int n = g.p * T + slot;
-  double* dp = S.band.Dp(n);
-  double* up = S.band.Up(n);
-  double* rp = S.band.Rp(n);
+    for (int a = 0; a < D; ++a) {
+      thc[a] = (double)tp[a];
+      thp[a] = (t > 0) ? (double)tp[a - D] : 0.0;
+      thn[a] = (t < T - 1) ? (double)tp[a + D] : 0.0;
+    }
+    NodeOut<DOF> o;
+    assemble_node<DOF, IO>(P, Wt, b, t, thp, thc, thn, start + (size_t)b * D, goal + (size_t)b * D,
+                           sdf + (size_t)b * P.sdf_sb, o);
+    double* nd = S.nodes + (size_t)m * N::kStride;
 #pragma unroll
-  for (int a = 0; a < D; ++a) {
-#pragma unroll
-    for (int c = 0; c <= a; ++c) dp[tri(a, c) * NN] = o.Dm[a][c];
-#pragma unroll
-    for (int c = 0; c < D; ++c) up[(a * D + c) * NN] = o.Um[a][c];
-    rp[a * NN] = o.r[a];
-  }
-  S.errp[n] = o.err;
-  S.errp[NN + n] = o.err_ext;
+    for (int a = 0; a < D; ++a) {
+      st_vec<D>(nd + N::oD + a * D, o.Dm[a]);
+      st_vec<D>(nd + N::oU + a * D, o.Um[a]);
+    }
+    st_vec<D>(nd + N::oR, o.r);
+    sts2(nd + N::oX, o.err, o.err_ext);
   }
 }
 
-// Deterministic per-problem sum of `vals[p*T .. p*T+T)` by warp w for problems w, w+nwarps, ...
-// `f(p, sum)` is called by lane 0.
+// Deterministic per-problem reduction by warp w for problems w, w+nwarps, ...: sum over the T
+// values `base[(p*T + i) * stride]`.  `f(p, sum)` is called by lane 0.
 template <typename F>
-__device__ __forceinline__ void reduce_per_problem(const double* vals, int np, int T, F f) {
+__device__ __forceinline__ void reduce_per_problem(const double* base, int stride, int np, int T, F f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int p = warp; p < np; p += nwarps) {
     double s = 0.0;
-    for (int i = lane; i < T; i += 32) s += vals[p * T + i];
+    for (int i = lane; i < T; i += 32) s += base[(size_t)(p * T + i) * stride];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) f(p, s);
   }
 }
 
-template <int D, int NN, typename IO>
-__device__ __forceinline__ void cta_prologue(const StepSmem<D, NN, IO>& S, int T, int NP, int np,
+template <int D, typename IO>
+__device__ __forceinline__ void cta_prologue(const KParams& P, const StepSmem<D, IO>& S, int T, int NP, int np,
                                              const IO* __restrict__ th_src, bool solve) {
-  if (threadIdx.x == 0) {
-    BcrLevels lv;
-    bcr_make_levels(T, lv);
-    for (int l = 0; l <= lv.nlev + 1; ++l) S.lvl_off[l] = lv.off[l];
-    S.lvl_off[kMaxLevels + 1] = lv.nlev;
-  }
+  if (threadIdx.x < kMaxLevels + 2) S.lvl_off[threadIdx.x] = P.lvl_off[threadIdx.x];   // host-computed level table
   for (int p = threadIdx.x; p < NP; p += blockDim.x) {
     S.fail[p] = 0;
     if (solve) { S.flags[p] = 0; S.flags[NP + p] = 0; }
@@ -142,82 +114,97 @@ __device__ __forceinline__ void cta_prologue(const StepSmem<D, NN, IO>& S, int T
   for (int i = threadIdx.x; i < n; i += blockDim.x) S.th[i] = __ldg(th_src + i);
 }
 
+#ifdef DGPMP2_TIMING
+// Debug builds only (-DDGPMP2_TIMING): per-phase clock64() stamps of CTA 0 / thread 0.
+__device__ long long g_phase_clock[64];
+__device__ void g_phase_clock_fwd(int i) { g_phase_clock[i] = clock64(); }
+#define DGPMP2_STAMP(i) do { if (blockIdx.x == (DGPMP2_TIMING - 1) && threadIdx.x == 0) g_phase_clock[i] = clock64(); } while (0)
+#else
+#define DGPMP2_STAMP(i) do { } while (0)
+#endif
+
 // One fused Gauss-Newton iteration.  grid = ceil(B / NP), block = NP * TPP threads (rounded to a warp).
-template <int DOF, int NN, int LPN, typename IO>
-__global__ void __launch_bounds__((StepShape<2 * DOF, NN, LPN>::kMaxThreads), (StepShape<2 * DOF, NN, LPN>::kMinBlocks))
+template <int DOF, typename IO>
+__global__ void __launch_bounds__(DOF == 2 ? 512 : 256)
 gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th, const IO* __restrict__ start,
                const IO* __restrict__ goal, const IO* __restrict__ sdf, IO* __restrict__ dth,
-               IO* __restrict__ err, IO* __restrict__ err_ext, int* __restrict__ status, const int NP, const int TPP) {
+               IO* __restrict__ err, IO* __restrict__ err_ext, int* __restrict__ status, const int NP) {
   constexpr int D = 2 * DOF;
+  using N = Node<D>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  StepSmem<D, NN, IO> S;
+  StepSmem<D, IO> S;
   const int T = P.T;
-  S.carve(smem_raw, false);
+  S.carve(smem_raw, NP, T, false);
   const int b0 = blockIdx.x * NP;
   const int np = min(NP, P.B - b0);
-  const CtaGeom g = cta_geom(TPP, np);
+  DGPMP2_STAMP(0);
 
-  cta_prologue<D, NN, IO>(S, T, NP, np, th + (size_t)b0 * T * D, false);
+  cta_prologue<D, IO>(P, S, T, NP, np, th + (size_t)b0 * T * D, false);
   __syncthreads();
-  const int nlev = S.lvl_off[kMaxLevels + 1];
+  const int nlev = P.nlev;
+  DGPMP2_STAMP(1);
 
-  assemble_cta<DOF, NN, IO>(P, Wt, S, b0, g, TPP, nlev, start, goal, sdf);
+  assemble_cta<DOF, IO>(P, Wt, S, b0, np, nlev, start, goal, sdf);
   __syncthreads();
+  DGPMP2_STAMP(2);
 
-  bcr_solve<D, NN, LPN>(S.band, S.lvl_off, nlev, T, g.active, g.p, g.u, TPP / LPN, S.fail);   // ends with a barrier
+  bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, S.fail);   // ends with a barrier
+  DGPMP2_STAMP(3);
 
   {  // dth, natural order -> coalesced stores
     IO* dst = dth + (size_t)b0 * T * D;
-    const int n = np * T * D;
+    const int n = np * T;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int a = i % D, pt = i / D;
-      const int p = pt / T, t = pt - p * T;
-      dst[i] = (IO)S.band.Rp(p * T + bcr_slot(S.lvl_off, T, t))[a * NN];
+      const int p = i / T, t = i - p * T;
+      double x[D];
+      ld_vec<D>(S.nodes + ((size_t)p * T + bcr_slot(S.lvl_off, T, t)) * N::kStride + N::oR, x);
+#pragma unroll
+      for (int a = 0; a < D; ++a) dst[(size_t)i * D + a] = (IO)x[a];
     }
   }
   const double invM = 1.0 / (double)P.M;
-  reduce_per_problem(S.errp, np, T, [&](int p, double s) { err[b0 + p] = (IO)(s * invM); });
-  reduce_per_problem(S.errp + NN, np, T, [&](int p, double s) { err_ext[b0 + p] = (IO)(s * invM); });
+  reduce_per_problem(S.nodes + N::oX, N::kStride, np, T, [&](int p, double s) { err[b0 + p] = (IO)(s * invM); });
+  reduce_per_problem(S.nodes + N::oX + 1, N::kStride, np, T, [&](int p, double s) { err_ext[b0 + p] = (IO)(s * invM); });
   if (status != nullptr)
     for (int p = threadIdx.x; p < np; p += blockDim.x) status[b0 + p] = S.fail[p];
+  DGPMP2_STAMP(4);
 }
 
 // ---------------------------------------------------------------------------
 // Persistent solve-to-convergence (DiffGPMP2Planner.forward, diff_gpmp2_planner.py:104-165)
 // ---------------------------------------------------------------------------
-template <int DOF, int NN, int LPN, typename IO>
-__global__ void __launch_bounds__((StepShape<2 * DOF, NN, LPN>::kMaxThreads), (StepShape<2 * DOF, NN, LPN>::kMinBlocks))
+template <int DOF, typename IO>
+__global__ void __launch_bounds__(DOF == 2 ? 512 : 256)
 gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th_init, const IO* __restrict__ start,
                 const IO* __restrict__ goal, const IO* __restrict__ sdf, const int max_iters, const double tol_delta,
                 IO* __restrict__ th_final, int* __restrict__ iters, IO* __restrict__ err_pi, IO* __restrict__ err_ext_pi,
-                IO* __restrict__ err_final, IO* __restrict__ err_ext_final, int* __restrict__ status, const int NP,
-                const int TPP) {
+                IO* __restrict__ err_final, IO* __restrict__ err_ext_final, int* __restrict__ status, const int NP) {
   constexpr int D = 2 * DOF;
+  using N = Node<D>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  StepSmem<D, NN, IO> S;
+  StepSmem<D, IO> S;
   const int T = P.T;
-  S.carve(smem_raw, true);
+  S.carve(smem_raw, NP, T, true);
   int* done = S.flags;          // [NP]
   int* nit = S.flags + NP;      // [NP]
   const int b0 = blockIdx.x * NP;
   const int np = min(NP, P.B - b0);
-  const CtaGeom g = cta_geom(TPP, np);
 
-  cta_prologue<D, NN, IO>(S, T, NP, np, th_init + (size_t)b0 * T * D, true);
+  cta_prologue<D, IO>(P, S, T, NP, np, th_init + (size_t)b0 * T * D, true);
   __syncthreads();
-  const int nlev = S.lvl_off[kMaxLevels + 1];
+  const int nlev = P.nlev;
   const double invM = 1.0 / (double)P.M;
 
   for (int j = 0;; ++j) {
     // assemble at the current iterate; the errors at iterate j are a by-product
-    assemble_cta<DOF, NN, IO>(P, Wt, S, b0, g, TPP, nlev, start, goal, sdf);
+    assemble_cta<DOF, IO>(P, Wt, S, b0, np, nlev, start, goal, sdf);
     __syncthreads();
     const bool last = (j >= max_iters);
-    reduce_per_problem(S.errp, np, T, [&](int p, double s) {
+    reduce_per_problem(S.nodes + N::oX, N::kStride, np, T, [&](int p, double s) {
       if (!done[p] && !last && err_pi != nullptr) err_pi[(size_t)(b0 + p) * max_iters + j] = (IO)(s * invM);
       if ((done[p] == 1 || last) && err_final != nullptr) err_final[b0 + p] = (IO)(s * invM);
     });
-    reduce_per_problem(S.errp + NN, np, T, [&](int p, double s) {
+    reduce_per_problem(S.nodes + N::oX + 1, N::kStride, np, T, [&](int p, double s) {
       if (!done[p] && !last && err_ext_pi != nullptr) err_ext_pi[(size_t)(b0 + p) * max_iters + j] = (IO)(s * invM);
       if ((done[p] == 1 || last) && err_ext_final != nullptr) err_ext_final[b0 + p] = (IO)(s * invM);
     });
@@ -230,19 +217,19 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
     for (int p = 0; p < np; ++p) all_done = all_done && (done[p] == 2);
     if (all_done || last) break;
 
-    bcr_solve<D, NN, LPN>(S.band, S.lvl_off, nlev, T, g.active, g.p, g.u, TPP / LPN, S.fail);
+    bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, S.fail);
 
     // th <- th + dth for problems still running; |dth|^2 partials
     for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
       const int p = m / T, t = m - p * T;
-      const int n = p * T + bcr_slot(S.lvl_off, T, t);
       double s2 = 0.0;
       if (!done[p]) {
+        double x[D];
+        ld_vec<D>(S.nodes + ((size_t)p * T + bcr_slot(S.lvl_off, T, t)) * N::kStride + N::oR, x);
 #pragma unroll
         for (int a = 0; a < D; ++a) {
-          const double dx = S.band.Rp(n)[a * NN];
           // the reference adds dtheta (I/O dtype) to th (I/O dtype): round dth first, then add
-          const IO dxi = (IO)dx;
+          const IO dxi = (IO)x[a];
           s2 += (double)dxi * (double)dxi;
           IO* q = S.th + ((size_t)p * T + t) * D + a;
           *q = (IO)(*q + dxi);
@@ -251,7 +238,7 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
       S.nrm[m] = s2;
     }
     __syncthreads();
-    reduce_per_problem(S.nrm, np, T, [&](int p, double s) {
+    reduce_per_problem(S.nrm, 1, np, T, [&](int p, double s) {
       if (!done[p]) {
         nit[p] = j + 1;
         // check_convergence (planner_utils.py:3-16): ||dtheta|| < tol_delta  or  j+1 >= max_iters
