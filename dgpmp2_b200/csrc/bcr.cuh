@@ -25,11 +25,11 @@
 // words, so all traffic is 128-bit LDS/STS and a quarter-warp touching 8 consecutive
 // records is bank-conflict free.
 //
-// Work decomposition.  Every problem owns TPP threads; work item e of a level (one
-// node) is processed by LPN = 2 lanes that split its column pairs (elimination) or
-// row pairs (Schur update).  Lanes never exchange registers: everything goes through
-// the records, ordered by __syncwarp inside an item and by the two CTA barriers per
-// level.
+// Work decomposition.  The work items of a level (one node each) are enumerated across
+// all problems of the CTA and each is processed by LPN = 4 adjacent lanes that split its
+// columns (elimination), rows (Schur update) or rows of the right-hand side (back
+// substitution).  Lanes never exchange registers: everything goes through the records,
+// ordered by __syncwarp inside an item and by the two CTA barriers per level.
 #pragma once
 #include "factors.cuh"
 
@@ -40,7 +40,7 @@
 namespace dgpmp2 {
 
 constexpr int kMaxLevels = 16;
-constexpr int kLPN = 2;
+constexpr int kLPN = 4;
 
 __host__ __device__ __forceinline__ int bcr_n_elim(int T, int s) { return (T + s - 1) / (2 * s); }   // nodes j = s(2q+1) < T
 __host__ __device__ __forceinline__ int bcr_n_kept(int T, int s) { return (T + 2 * s - 1) / (2 * s); } // nodes i = 2sq < T
@@ -58,11 +58,13 @@ __host__ __device__ inline void bcr_make_levels(int T, BcrLevels& lv) {
   lv.nlev = l - 1;
 }
 
-// slot of trajectory state t inside its problem
-__device__ __forceinline__ int bcr_slot(const int* off, int T, int t) {
-  if (t == 0) return T - 1;
-  const int l = __ffs(t);          // ctz(t) + 1 = level at which t is eliminated
-  return off[l] + (t >> l);
+// slot of trajectory state t inside its problem.  Closed form of off[l] + (t >> l) with
+// l = ctz(t) + 1 and off[l] = #{1 <= u < T : ctz(u) + 1 < l} = (T-1) - ((T-1) >> (l-1)); the table
+// argument is kept for the host-side / test model but not read on the device.
+__device__ __forceinline__ int bcr_slot(const int* /*off*/, int T, int t) {
+  const int z = __ffs(t) - 1;      // ctz(t); -1 for t == 0
+  const int s = (T - 1) - ((T - 1) >> z) + (t >> (z + 1));
+  return (t == 0) ? (T - 1) : s;
 }
 // inverse: trajectory state stored in slot m
 __device__ __forceinline__ int bcr_state_of_slot(const int* off, int nlev, int T, int m) {
@@ -176,6 +178,21 @@ __device__ __forceinline__ void ld_lower(const double* p, double (&L)[D * (D + 1
 // exact floor(e / n) for 0 <= e < 2^20, 1 <= n <= 2^12 with inv = 1.0f / n (error analysis: the
 // quotient (e + 0.5) / n is at least 0.5 / n away from an integer, the float error is < 2^-22 * e / n)
 __device__ __forceinline__ int fast_div(int e, float inv) { return __float2int_rz(((float)e + 0.5f) * inv); }
+// m / n and m % n for a divisor n that is the same for the whole level: a shift when n is a power of two
+struct LevelDiv {
+  int n, sh; float inv;
+  __device__ __forceinline__ void split(int m, int& q, int& r) const {
+    q = (sh >= 0) ? (m >> sh) : fast_div(m, inv);
+    r = m - q * n;
+  }
+};
+__device__ __forceinline__ LevelDiv make_level_div(int n) {
+  LevelDiv d;
+  d.n = n;
+  d.sh = ((n & (n - 1)) == 0) ? (__ffs(n) - 1) : -1;
+  d.inv = 1.0f / (float)n;
+  return d;
+}
 
 // Factor + solve the CTA's np problems.  `nodes` = first record of problem 0 (np * T records,
 // problem-major).  The work items of a level are enumerated across ALL problems of the CTA
@@ -188,8 +205,8 @@ template <int D>
 __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int* __restrict__ lvl_off, int nlev,
                                           int T, int np, int* fail) {
   using N = Node<D>;
-  constexpr int DS = N::DS, S = N::kStride, LPN = kLPN, NP2 = D / 2;   // NP2 column / row pairs
-  constexpr int NPL = (NP2 + LPN - 1) / LPN;                           // pairs per lane
+  constexpr int DS = N::DS, S = N::kStride, LPN = kLPN;
+  constexpr int NCL = (D + LPN - 1) / LPN;                             // columns / rows per lane
   const int e0 = threadIdx.x / LPN, lane = threadIdx.x % LPN;
   const int EPP = blockDim.x / LPN;
 
@@ -198,14 +215,15 @@ __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int*
   for (int l = 1; l <= nlev; ++l) {
     const int s = 1 << (l - 1);
     const int ne = (T + s - 1) >> l;          // bcr_n_elim(T, s), 2s = 2^l
-    // (a) factor the eliminated nodes; lanes split the column pairs of [U_i^T | U_j]
-    const float inv_ne = 1.0f / (float)ne;
-    for (int m = e0;; m += EPP) {
+    // (a) factor the eliminated nodes; the lanes of an item split the columns of [U_i^T | U_j]
+    const LevelDiv dv_e = make_level_div(ne);
+    for (int base = 0; base < np * ne; base += EPP) {   // uniform trip count for the whole CTA
+      const int m = base + e0;
       const bool on = m < np * ne;
       const unsigned m_el = __ballot_sync(0xffffffffu, on);
-      if (m_el == 0u) break;                  // warp-uniform
       if (on) {
-        const int p = fast_div(m, inv_ne), e = m - p * ne;
+        int p, e;
+        dv_e.split(m, p, e);
         double* pn = nodes + (size_t)p * T * S;
         const int j = s * (2 * e + 1);
         double* nj = pn + (size_t)(off_l + e) * S;
@@ -213,20 +231,15 @@ __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int*
         const bool has_right = (j + s) < T;
         double L[DS];
         ld_lower<D>(nj + N::oD, L);
-        // this lane's column pairs: issue their loads before the Cholesky chain
-        double ve[NPL][2][D], vf[NPL][2][D], vg[D];
+        // this lane's columns: issue their loads before the Cholesky chain
+        double ve[NCL][D], vf[NCL][D], vg[D];
 #pragma unroll
-        for (int q = 0; q < NPL; ++q) {
-          const int cp = lane + q * LPN;
-          if (cp < NP2) {
-            ld_vec<D>(ni + N::oU + (2 * cp) * D, ve[q][0]);          // row c of U_i = column c of U_i^T
-            ld_vec<D>(ni + N::oU + (2 * cp + 1) * D, ve[q][1]);
+        for (int q = 0; q < NCL; ++q) {
+          const int c = lane + q * LPN;
+          if (c < D) {
+            ld_vec<D>(ni + N::oU + c * D, ve[q]);                     // row c of U_i = column c of U_i^T
 #pragma unroll
-            for (int a = 0; a < D; ++a) {                             // columns (2cp, 2cp+1) of U_j, row-major
-              const double2 t = lds2(nj + N::oU + a * D + 2 * cp);
-              vf[q][0][a] = has_right ? t.x : 0.0;
-              vf[q][1][a] = has_right ? t.y : 0.0;
-            }
+            for (int a = 0; a < D; ++a) vf[q][a] = has_right ? nj[N::oU + a * D + c] : 0.0;   // column c of U_j (row-major)
           }
         }
         ld_vec<D>(nj + N::oR, vg);
@@ -237,100 +250,79 @@ __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int*
           for (int k = 0; k < DS; k += 2) sts2(nj + N::oD + k, L[k], (k + 1 < DS) ? L[k + 1] : 0.0);
         }
 #pragma unroll
-        for (int q = 0; q < NPL; ++q) {
-          const int cp = lane + q * LPN;
-          if (cp < NP2) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              fwd_solve<D>(L, ve[q][h]);
-              fwd_solve<D>(L, vf[q][h]);
-              st_vec<D>(nj + N::oE + (2 * cp + h) * D, ve[q][h]);    // column of E_j, column-major
-              st_vec<D>(nj + N::oU + (2 * cp + h) * D, vf[q][h]);    // column of F_j, column-major, in place
-            }
+        for (int q = 0; q < NCL; ++q) {
+          const int c = lane + q * LPN;
+          if (c < D) {
+            fwd_solve<D>(L, ve[q]);
+            fwd_solve<D>(L, vf[q]);
+            st_vec<D>(nj + N::oE + c * D, ve[q]);                     // column c of E_j, column-major
+            st_vec<D>(nj + N::oU + c * D, vf[q]);                     // column c of F_j, column-major, in place
           }
         }
-        if (lane == 0) {
-          fwd_solve<D>(L, vg);
-          st_vec<D>(nj + N::oR, vg);
-        }
+        fwd_solve<D>(L, vg);
+        if (lane == 0) st_vec<D>(nj + N::oR, vg);
       }
     }
     __syncthreads();
     DGPMP2_BCR_STAMP(8 + 2 * l);
-    // (b) Schur-complement update of the kept nodes; lanes split the row pairs of (D_i, r_i, U_i')
+    // (b) Schur-complement update of the kept nodes; the lanes of an item split the rows of (D_i, r_i, U_i')
     const int nk = (T + 2 * s - 1) >> l;      // bcr_n_kept(T, s)
-    const float inv_nk = 1.0f / (float)nk;
+    const LevelDiv dv_k = make_level_div(nk);
     for (int m = e0; m < np * nk; m += EPP) {
-      {
-        const int p = fast_div(m, inv_nk), e = m - p * nk;
-        double* pn = nodes + (size_t)p * T * S;
-        const int i = 2 * s * e;
-        double* ni = pn + (size_t)bcr_slot(lvl_off, T, i) * S;
-        const bool has_l = e > 0, has_r = (i + s) < T, has_rr = (i + 2 * s) < T;
-        const double* nl = pn + (size_t)(off_l + (has_l ? e - 1 : 0)) * S;   // j = i - s
-        const double* nr = pn + (size_t)(off_l + (has_r ? e : 0)) * S;       // j = i + s
+      int p, e;
+      dv_k.split(m, p, e);
+      double* pn = nodes + (size_t)p * T * S;
+      const int i = 2 * s * e;
+      double* ni = pn + (size_t)bcr_slot(lvl_off, T, i) * S;
+      const bool has_l = e > 0, has_r = (i + s) < T, has_rr = (i + 2 * s) < T;
+      const double* nl = pn + (size_t)(off_l + (has_l ? e - 1 : 0)) * S;   // j = i - s
+      const double* nr = pn + (size_t)(off_l + (has_r ? e : 0)) * S;       // j = i + s
 #pragma unroll
-        for (int q = 0; q < NPL; ++q) {
-          const int rp = lane + q * LPN;
-          if (rp < NP2) {
-            const int a0 = 2 * rp;
-            double d0[D], d1[D], r0, r1;
-            ld_vec<D>(ni + N::oD + a0 * D, d0);
-            ld_vec<D>(ni + N::oD + (a0 + 1) * D, d1);
-            {
-              const double2 t = lds2(ni + N::oR + a0);
-              r0 = t.x; r1 = t.y;
-            }
-            if (has_l) {   // D_i -= F^T F, r_i -= F^T g with F (column-major), g of j = i - s
-              double fa0[D], fa1[D], g[D];
-              ld_vec<D>(nl + N::oU + a0 * D, fa0);
-              ld_vec<D>(nl + N::oU + (a0 + 1) * D, fa1);
-              ld_vec<D>(nl + N::oR, g);
+      for (int q = 0; q < NCL; ++q) {
+        const int a = lane + q * LPN;
+        if (a < D) {
+          double drow[D], unew[D], ra;
+          ld_vec<D>(ni + N::oD + a * D, drow);
+          ra = ni[N::oR + a];
 #pragma unroll
-              for (int k = 0; k < D; ++k) { r0 -= fa0[k] * g[k]; r1 -= fa1[k] * g[k]; }
+          for (int c = 0; c < D; ++c) unew[c] = 0.0;
+          if (has_l) {   // D_i -= F^T F, r_i -= F^T g with F (column-major), g of j = i - s
+            double fa[D], g[D];
+            ld_vec<D>(nl + N::oU + a * D, fa);
+            ld_vec<D>(nl + N::oR, g);
 #pragma unroll
-              for (int c = 0; c < D; ++c) {
-                double fc[D];
-                ld_vec<D>(nl + N::oU + c * D, fc);
-                double s0 = 0.0, s1 = 0.0;
+            for (int k = 0; k < D; ++k) ra -= fa[k] * g[k];
 #pragma unroll
-                for (int k = 0; k < D; ++k) { s0 += fa0[k] * fc[k]; s1 += fa1[k] * fc[k]; }
-                d0[c] -= s0; d1[c] -= s1;
-              }
-            }
-            double u0[D], u1[D];
+            for (int c = 0; c < D; ++c) {
+              double fc[D];
+              ld_vec<D>(nl + N::oU + c * D, fc);
+              double s0 = 0.0;
 #pragma unroll
-            for (int c = 0; c < D; ++c) { u0[c] = 0.0; u1[c] = 0.0; }
-            if (has_r) {   // D_i -= E^T E, r_i -= E^T g, U_i' = -E^T F with E, F, g of j = i + s
-              double ea0[D], ea1[D], g[D];
-              ld_vec<D>(nr + N::oE + a0 * D, ea0);
-              ld_vec<D>(nr + N::oE + (a0 + 1) * D, ea1);
-              ld_vec<D>(nr + N::oR, g);
-#pragma unroll
-              for (int k = 0; k < D; ++k) { r0 -= ea0[k] * g[k]; r1 -= ea1[k] * g[k]; }
-#pragma unroll
-              for (int c = 0; c < D; ++c) {
-                double ec[D], fc[D];
-                ld_vec<D>(nr + N::oE + c * D, ec);
-                ld_vec<D>(nr + N::oU + c * D, fc);
-                double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                  s0 += ea0[k] * ec[k]; s1 += ea1[k] * ec[k];
-                  t0 += ea0[k] * fc[k]; t1 += ea1[k] * fc[k];
-                }
-                d0[c] -= s0; d1[c] -= s1;
-                u0[c] = -t0; u1[c] = -t1;
-              }
-            }
-            st_vec<D>(ni + N::oD + a0 * D, d0);
-            st_vec<D>(ni + N::oD + (a0 + 1) * D, d1);
-            sts2(ni + N::oR + a0, r0, r1);
-            if (has_rr) {
-              st_vec<D>(ni + N::oU + a0 * D, u0);          // new coupling to i + 2s, row-major
-              st_vec<D>(ni + N::oU + (a0 + 1) * D, u1);
+              for (int k = 0; k < D; ++k) s0 += fa[k] * fc[k];
+              drow[c] -= s0;
             }
           }
+          if (has_r) {   // D_i -= E^T E, r_i -= E^T g, U_i' = -E^T F with E, F, g of j = i + s
+            double ea[D], g[D];
+            ld_vec<D>(nr + N::oE + a * D, ea);
+            ld_vec<D>(nr + N::oR, g);
+#pragma unroll
+            for (int k = 0; k < D; ++k) ra -= ea[k] * g[k];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              double ec[D], fc[D];
+              ld_vec<D>(nr + N::oE + c * D, ec);
+              ld_vec<D>(nr + N::oU + c * D, fc);
+              double s0 = 0.0, t0 = 0.0;
+#pragma unroll
+              for (int k = 0; k < D; ++k) { s0 += ea[k] * ec[k]; t0 += ea[k] * fc[k]; }
+              drow[c] -= s0;
+              unew[c] = -t0;
+            }
+          }
+          st_vec<D>(ni + N::oD + a * D, drow);
+          ni[N::oR + a] = ra;
+          if (has_rr) st_vec<D>(ni + N::oU + a * D, unew);           // new coupling to i + 2s, row-major
         }
       }
     }
@@ -358,44 +350,55 @@ __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int*
     const int s = 1 << (l - 1);
     const int ne = (T + s - 1) >> l;
     off_l -= ne;
-    const float inv_ne = 1.0f / (float)ne;
-    for (int m = e0;; m += EPP) {
+    const LevelDiv dv_e = make_level_div(ne);
+    for (int base = 0; base < np * ne; base += EPP) {
+      const int m = base + e0;
       const bool on = m < np * ne;
       const unsigned m_bs = __ballot_sync(0xffffffffu, on);
-      if (m_bs == 0u) break;
       if (on) {
-        const int p = fast_div(m, inv_ne), e = m - p * ne;
+        int p, e;
+        dv_e.split(m, p, e);
         double* pn = nodes + (size_t)p * T * S;
         const int j = s * (2 * e + 1);
         double* nj = pn + (size_t)(off_l + e) * S;
         const double* ni = pn + (size_t)bcr_slot(lvl_off, T, j - s) * S;
         const bool has_right = (j + s) < T;
         const double* nk2 = has_right ? pn + (size_t)bcr_slot(lvl_off, T, j + s) * S : ni;
-        double xl[D], xr[D], v[D], L[DS];
+        double xl[D], xr[D], L[DS];
         ld_vec<D>(ni + N::oR, xl);
         ld_vec<D>(nk2 + N::oR, xr);
-        ld_vec<D>(nj + N::oR, v);
+#pragma unroll
+        for (int c = 0; c < D; ++c) xr[c] = has_right ? xr[c] : 0.0;
 #pragma unroll
         for (int k = 0; k < DS; k += 2) {
           const double2 t = lds2(nj + N::oD + k);
           L[k] = t.x;
           if (k + 1 < DS) L[k + 1] = t.y;
         }
+        // each lane forms its rows of v = g_j - E_j x_{j-s} - F_j x_{j+s} and publishes them in place of g_j
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
-          double ec[D], fc[D];
-          ld_vec<D>(nj + N::oE + c * D, ec);
-          ld_vec<D>(nj + N::oU + c * D, fc);
-          const double xrc = has_right ? xr[c] : 0.0;
+        for (int q = 0; q < NCL; ++q) {
+          const int a = lane + q * LPN;
+          if (a < D) {
+            double va = nj[N::oR + a], vb = 0.0;
 #pragma unroll
-          for (int a = 0; a < D; ++a) v[a] -= ec[a] * xl[c] + fc[a] * xrc;
+            for (int c = 0; c < D; ++c) {
+              va -= nj[N::oE + c * D + a] * xl[c];
+              vb -= nj[N::oU + c * D + a] * xr[c];
+            }
+            nj[N::oR + a] = va + vb;
+          }
         }
+        __syncwarp(m_bs);
+        double v[D];
+        ld_vec<D>(nj + N::oR, v);
         bwd_solve<D>(L, v);
-        __syncwarp(m_bs);   // all lanes have read g_j before any lane overwrites it with x_j
-        // every lane holds the full x_j; lane ln stores the pairs ln, ln + LPN, ...
+        __syncwarp(m_bs);   // all lanes have read v before any lane overwrites it with x_j
 #pragma unroll
-        for (int rp = 0; rp < NP2; ++rp)
-          if ((rp % LPN) == lane) sts2(nj + N::oR + 2 * rp, v[2 * rp], v[2 * rp + 1]);
+        for (int q = 0; q < NCL; ++q) {
+          const int a = lane + q * LPN;
+          if (a < D) nj[N::oR + a] = v[a];
+        }
       }
     }
     __syncthreads();

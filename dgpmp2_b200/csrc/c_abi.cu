@@ -50,6 +50,7 @@ KParams make_kparams(const dgpmp2_params* p) {
   if (p->flags & DGPMP2_FLAG_VEL_LIMITS) k.M += p->dof * p->T;
   k.sdf_sb = p->sdf_stride_b;
   k.res = p->res;
+  k.inv_res = 1.0 / p->res;
   k.orig_x = 0.0 - p->x_lo / p->res;          // sdf_utils.py:57
   k.orig_y = 0.0 - p->y_lo / p->res;          // sdf_utils.py:58
   k.dt = p->dt;

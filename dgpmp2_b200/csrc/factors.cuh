@@ -22,6 +22,7 @@ struct KParams {
   int B, T, H, W, flags, M;
   long long sdf_sb;
   double orig_x, orig_y, res;      // sdf_utils.py:57-58, obstacle_cost.py:34
+  double inv_res;                  // 1 / res (gradient scaling only; pixel coordinates use the exact division)
   double dt, qa, qb, qc;           // 12 dt^-3, -6 dt^-2, 4 dt^-1   (gp_factor.py:66-68)
   double r_sphere, ks, kg, reg, kd, kv, vx_lim, vy_lim;
   double qc_const[9], qc_fix[9];
@@ -56,10 +57,12 @@ template <typename IO> __device__ __forceinline__ double ldg_d(const IO* p) { re
 // ---------------------------------------------------------------------------
 struct SdfSample { double dist, Jx, Jy; };   // J as returned by bilinear_interpolate
 
-template <typename IO>
+// EXACT_J: divide the gradient by res exactly as the reference does (bilinear_interpolate API, bit-exact J);
+// otherwise multiply by 1/res (<= 1 ulp difference, no branch depends on J) -- used inside the GN kernels.
+template <typename IO, bool EXACT_J = true>
 __device__ __forceinline__ SdfSample sdf_bilinear(const IO* __restrict__ sdf, int H, int W,
                                                   double orig_x, double orig_y, double res,
-                                                  double x, double y) {
+                                                  double x, double y, double inv_res = 0.0) {
   // px = orig_x + x / res ; py = orig_y - y / res   (true divisions, reference order)
   const double px = __dadd_rn(orig_x, __ddiv_rn(x, res));
   const double py = __dsub_rn(orig_y, __ddiv_rn(y, res));
@@ -84,8 +87,13 @@ __device__ __forceinline__ SdfSample sdf_bilinear(const IO* __restrict__ sdf, in
   // J[:, :, 0] = -1*(wja*(v21-v11) + wjb*(v22-v12))/res ; J[:, :, 1] = (wjc*(v12-v11) + wjd*(v22-v21))/res  (:93-94)
   const double gx = __dadd_rn(__dmul_rn(ay, __dsub_rn(v21, v11)), __dmul_rn(by, __dsub_rn(v22, v12)));
   const double gy = __dadd_rn(__dmul_rn(ax, __dsub_rn(v12, v11)), __dmul_rn(bx, __dsub_rn(v22, v21)));
-  s.Jx = __ddiv_rn(-gx, res);
-  s.Jy = __ddiv_rn(gy, res);
+  if (EXACT_J) {
+    s.Jx = __ddiv_rn(-gx, res);
+    s.Jy = __ddiv_rn(gy, res);
+  } else {
+    s.Jx = -gx * inv_res;
+    s.Jy = gy * inv_res;
+  }
   return s;
 }
 
@@ -351,7 +359,7 @@ __device__ __forceinline__ void assemble_node(const KParams& P, const KWeights<I
     const double eps = (Wt.eps != nullptr) ? ldg_d(Wt.eps + (long long)b * Wt.e_sb + (long long)t * Wt.e_st) : P.eps_const;
     const double w = (Wt.w != nullptr) ? ldg_d(Wt.w + (long long)b * Wt.w_sb + (long long)t * Wt.w_st) : P.w_const;
     const double eps_tot = __dadd_rn(eps, P.r_sphere);
-    const SdfSample s = sdf_bilinear<IO>(sdf_b, P.H, P.W, P.orig_x, P.orig_y, P.res, th[0], th[1]);
+    const SdfSample s = sdf_bilinear<IO, false>(sdf_b, P.H, P.W, P.orig_x, P.orig_y, P.res, th[0], th[1], P.inv_res);
     const ObsTerm ob = hinge(s, eps_tot);
     o.Dm[0][0] += w * ob.hx * ob.hx;
     o.Dm[0][1] += w * ob.hx * ob.hy;

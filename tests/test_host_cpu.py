@@ -58,12 +58,13 @@ def test_launch_shape_and_limits():
     from dgpmp2_b200 import _lib, ops
     mk = lambda T, dof=2, B=1024: _lib.make_params(B, T, dof, 16, 16, (-5, 5), (-5, 5), 10.0, 0.4, 0.01, 0.01, 0.1, torch.eye(dof), 0.01, 0.4)
     s = ops.launch_shape(mk(64))
-    # one problem per CTA, two lanes per level-1 BCR item, and 7 CTAs (>= 1024 / 148) fit in one SM's shared memory
-    assert s['problems_per_cta'] == 1 and s['grid'] == 1024 and s['threads'] == 64
-    assert 7 * (s['smem_bytes'] + 1024) <= 233472
-    assert ops.launch_shape(mk(8))['problems_per_cta'] == 8       # short problems share a CTA
-    assert ops.launch_shape(mk(128))['grid'] == 1024 and ops.launch_shape(mk(128))['threads'] == 128
-    assert ops.launch_shape(mk(96, dof=3, B=512))['grid'] == 512
+    # the ceil(1024 / 148) = 7 problems an SM has to process share ONE CTA (packed BCR items), 147 CTAs on 148 SMs
+    assert s['problems_per_cta'] == 7 and s['grid'] == 147 and s['threads'] == 512
+    assert s['smem_bytes'] <= 232448
+    assert ops.launch_shape(mk(64, B=8))['problems_per_cta'] == 1   # small batches: one problem per CTA, 4 lanes per item
+    assert ops.launch_shape(mk(64, B=8))['threads'] == 128
+    assert ops.launch_shape(mk(128))['problems_per_cta'] == 3       # bounded by shared memory
+    assert ops.launch_shape(mk(96, dof=3, B=512))['problems_per_cta'] == 2
     assert ops.launch_shape(mk(512))['smem_bytes'] <= 232448
     with pytest.raises(_lib.Dgpmp2Error):
         ops.launch_shape(mk(600))             # longer than the on-chip band: documented limit
