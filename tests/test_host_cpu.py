@@ -63,7 +63,7 @@ def test_launch_shape_and_limits():
     assert s['smem_bytes'] <= 232448
     assert ops.launch_shape(mk(64, B=8))['problems_per_cta'] == 1   # small batches: one problem per CTA, 4 lanes per item
     assert ops.launch_shape(mk(64, B=8))['threads'] == 128
-    assert ops.launch_shape(mk(128))['problems_per_cta'] == 3       # bounded by shared memory
+    assert ops.launch_shape(mk(128))['problems_per_cta'] == 4       # bounded by shared memory (7 would not fit)
     assert ops.launch_shape(mk(96, dof=3, B=512))['problems_per_cta'] == 2
     assert ops.launch_shape(mk(512))['smem_bytes'] <= 232448
     with pytest.raises(_lib.Dgpmp2Error):
