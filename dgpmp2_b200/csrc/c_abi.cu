@@ -142,15 +142,15 @@ int sm_count() {
 // of all of them are packed onto consecutive lanes, so the sparse deep levels of several problems
 // share warps, and one CTA per SM launches without a ramp.  Threads = kLPN lanes per level-1 item.
 template <int D, typename IO>
-int choose_shape(int B, int T, bool solve, LaunchShape& s) {
+int choose_shape(int B, int T, int mode, LaunchShape& s) {
   const int max_threads = (D == 4) ? 512 : 256;
   const int items = (T + 1) / 2;                 // level-1 work items (and assembly needs T threads ~ 2 * items)
   int np = (B + sm_count() - 1) / sm_count();
   np = env_int("DGPMP2_NP", np);
   if (np > B) np = B;
   if (np < 1) np = 1;
-  while (np > 1 && StepSmem<D, IO>::bytes(np, T, solve) > (size_t)kSmemLimit) --np;
-  const size_t bytes = StepSmem<D, IO>::bytes(np, T, solve);
+  while (np > 1 && StepSmem<D, IO>::bytes(np, T, mode) > (size_t)kSmemLimit) --np;
+  const size_t bytes = StepSmem<D, IO>::bytes(np, T, mode);
   if (bytes > (size_t)kSmemLimit) return DGPMP2_ERR_UNSUPPORTED;
   int threads = kLPN * items * np;
   threads = (threads + 31) / 32 * 32;
@@ -189,7 +189,7 @@ template <int DOF, typename IO>
 int launch_step(const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start, const IO* goal, const IO* sdf,
                 IO* dth, IO* err, IO* err_ext, int32_t* status, cudaStream_t st) {
   LaunchShape s;
-  int rc = choose_shape<2 * DOF, IO>(k.B, k.T, false, s);
+  int rc = choose_shape<2 * DOF, IO>(k.B, k.T, 0, s);
   if (rc != DGPMP2_OK) return rc;
   auto kern = gn_step_kernel<DOF, IO>;
   rc = allow_smem(kern, s.smem);
@@ -219,7 +219,7 @@ int launch_solve(const KParams& k, const KWeights<IO>& kw, const IO* th, const I
                  int max_iters, double tol, IO* th_final, int32_t* iters, IO* epi, IO* eepi, IO* ef, IO* eef,
                  int32_t* status, cudaStream_t st) {
   LaunchShape s;
-  int rc = choose_shape<2 * DOF, IO>(k.B, k.T, true, s);
+  int rc = choose_shape<2 * DOF, IO>(k.B, k.T, 1, s);
   if (rc != DGPMP2_OK) return rc;
   auto kern = gn_solve_kernel<DOF, IO>;
   rc = allow_smem(kern, s.smem);
@@ -246,6 +246,42 @@ int gn_solve_impl(const dgpmp2_params* p, const IO* th, const IO* start, const I
   if (p->dof == 2)
     return launch_solve<2, IO>(k, kw, th, start, goal, sdf, max_iters, tol, th_final, iters, epi, eepi, ef, eef, status, st);
   return launch_solve<3, IO>(k, kw, th, start, goal, sdf, max_iters, tol, th_final, iters, epi, eepi, ef, eef, status, st);
+}
+
+template <int DOF, typename IO>
+int launch_bwd(const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start, const IO* goal, const IO* sdf,
+               const IO* dth, const IO* g_dth, const IO* g_err_ext, IO* g_th, IO* g_start, IO* g_goal, IO* g_qc, IO* g_w,
+               IO* g_eps, IO* g_sdf, long long g_sdf_sb, cudaStream_t st) {
+  LaunchShape s;
+  int rc = choose_shape<2 * DOF, IO>(k.B, k.T, 2, s);
+  if (rc != DGPMP2_OK) return rc;
+  auto kern = gn_step_bwd_kernel<DOF, IO>;
+  rc = allow_smem(kern, s.smem);
+  if (rc != DGPMP2_OK) return rc;
+  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, dth, g_dth, g_err_ext, g_th, g_start, g_goal, g_qc,
+                                          g_w, g_eps, g_sdf, g_sdf_sb, s.np);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
+}
+
+template <typename IO>
+int gn_step_backward_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO* goal, const IO* sdf,
+                          const dgpmp2_weights* w, const IO* dth, const IO* g_dth, const IO* g_err_ext, IO* g_th,
+                          IO* g_start, IO* g_goal, IO* g_qc, IO* g_w, IO* g_eps, IO* g_sdf, void* stream) {
+  int rc = check_params(p, w);
+  if (rc != DGPMP2_OK) return rc;
+  if (p->B == 0) return DGPMP2_OK;
+  if (!th || !start || !goal || !sdf || !dth || !g_dth) return DGPMP2_ERR_ARG;
+  KParams k = make_kparams(p);
+  const KWeights<IO> kw = make_kweights<IO>(w);
+  finish_kparams(k, kw);
+  k.static_gp = 0;   // the backward evaluates the GP blocks generically (it needs Q^-1 itself)
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->dof == 2)
+    return launch_bwd<2, IO>(k, kw, th, start, goal, sdf, dth, g_dth, g_err_ext, g_th, g_start, g_goal, g_qc, g_w, g_eps,
+                             g_sdf, p->sdf_stride_b, st);
+  return launch_bwd<3, IO>(k, kw, th, start, goal, sdf, dth, g_dth, g_err_ext, g_th, g_start, g_goal, g_qc, g_w, g_eps,
+                           g_sdf, p->sdf_stride_b, st);
 }
 
 template <typename IO>
@@ -417,6 +453,21 @@ int dgpmp2_gn_step_f64(const dgpmp2_params* p, const double* th, const double* s
   return gn_step_impl<double>(p, th, start, goal, sdf, w, dth, err, err_ext, status, stream);
 }
 
+int dgpmp2_gn_step_backward_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal,
+                                const float* sdf, const dgpmp2_weights* w, const float* dth, const float* g_dth,
+                                const float* g_err_ext, float* g_th, float* g_start, float* g_goal, float* g_qc,
+                                float* g_w, float* g_eps, float* g_sdf, void* stream) {
+  return gn_step_backward_impl<float>(p, th, start, goal, sdf, w, dth, g_dth, g_err_ext, g_th, g_start, g_goal, g_qc, g_w,
+                                      g_eps, g_sdf, stream);
+}
+int dgpmp2_gn_step_backward_f64(const dgpmp2_params* p, const double* th, const double* start, const double* goal,
+                                const double* sdf, const dgpmp2_weights* w, const double* dth, const double* g_dth,
+                                const double* g_err_ext, double* g_th, double* g_start, double* g_goal, double* g_qc,
+                                double* g_w, double* g_eps, double* g_sdf, void* stream) {
+  return gn_step_backward_impl<double>(p, th, start, goal, sdf, w, dth, g_dth, g_err_ext, g_th, g_start, g_goal, g_qc, g_w,
+                                       g_eps, g_sdf, stream);
+}
+
 int dgpmp2_gn_solve_f32(const dgpmp2_params* p, const float* th_init, const float* start, const float* goal,
                         const float* sdf, const dgpmp2_weights* w, int32_t max_iters, double tol_delta, float* th_final,
                         int32_t* iters, float* err_per_iter, float* err_ext_per_iter, float* err_final,
@@ -501,8 +552,8 @@ int dgpmp2_gn_step_launch_shape(const dgpmp2_params* p, int32_t elem_size, int32
   if (rc != DGPMP2_OK) return rc;
   LaunchShape s{0, 0, 0, 0, 0};
   const int B = p->B > 0 ? p->B : 1;
-  if (p->dof == 2) rc = (elem_size == 4) ? choose_shape<4, float>(B, p->T, false, s) : choose_shape<4, double>(B, p->T, false, s);
-  else rc = (elem_size == 4) ? choose_shape<6, float>(B, p->T, false, s) : choose_shape<6, double>(B, p->T, false, s);
+  if (p->dof == 2) rc = (elem_size == 4) ? choose_shape<4, float>(B, p->T, 0, s) : choose_shape<4, double>(B, p->T, 0, s);
+  else rc = (elem_size == 4) ? choose_shape<6, float>(B, p->T, 0, s) : choose_shape<6, double>(B, p->T, 0, s);
   if (rc != DGPMP2_OK) return rc;
   if (problems_per_cta) *problems_per_cta = s.np;
   if (threads) *threads = s.threads;

@@ -409,3 +409,210 @@ __device__ __forceinline__ void assemble_node(const KParams& P, const KWeights<I
 }
 
 }  // namespace dgpmp2
+
+// ===========================================================================
+// Backward of one GN step (reverse-mode derivative of dtheta = Lambda^-1 R and of err_ext).
+//
+// With lambda = Lambda^-1 gbar (gbar = dL/d dtheta, solved with the same BCR) every factor f with
+// Jacobian H_f, error e_f and weight K_f contributes, for a_f = H_f lambda (factor-space adjoint),
+// rho_f = e_f - H_f dtheta (linearised residual after the step), alpha_f = K_f a_f, beta_f = K_f rho_f:
+//     dL = alpha_f^T de_f + beta_f^T dH_f lambda - alpha_f^T dH_f dtheta + a_f^T dK_f rho_f
+// (from dL = lambda^T dR - lambda^T dLambda dtheta with Lambda = sum H^T K H + reg I, R = sum H^T K e).
+// err_ext = 0.5 sum e_f^T Kfix_f e_f / M adds  ghat Kfix_f e_f  to alpha_f in the de_f term only.
+// The reference obtains the same numbers by autograd through its dense solve (plan_layer.py:214-234).
+// ===========================================================================
+namespace dgpmp2 {
+
+struct SdfCell {       // everything the obstacle factor's backward needs
+  int x1, x2, y1, y2;
+  double ax, bx, ay, by, v11, v21, v12, v22, dist, hx, hy;   // h = grad dist = -J
+};
+
+template <typename IO>
+__device__ __forceinline__ SdfCell sdf_cell(const IO* __restrict__ sdf, int H, int W, double orig_x, double orig_y,
+                                            double res, double inv_res, double x, double y) {
+  SdfCell c;
+  const double px = __dadd_rn(orig_x, __ddiv_rn(x, res));
+  const double py = __dsub_rn(orig_y, __ddiv_rn(y, res));
+  const double fx = floor(px), fy = floor(py);
+  const double wm = (double)(W - 1), hm = (double)(H - 1);
+  const double x1d = fmin(fmax(fx, 0.0), wm), x2d = fmin(fmax(fx + 1.0, 0.0), wm);
+  const double y1d = fmin(fmax(fy, 0.0), hm), y2d = fmin(fmax(fy + 1.0, 0.0), hm);
+  c.x1 = (int)x1d; c.x2 = (int)x2d; c.y1 = (int)y1d; c.y2 = (int)y2d;
+  c.v11 = ldg_d(sdf + (long long)c.y1 * W + c.x1); c.v21 = ldg_d(sdf + (long long)c.y1 * W + c.x2);
+  c.v12 = ldg_d(sdf + (long long)c.y2 * W + c.x1); c.v22 = ldg_d(sdf + (long long)c.y2 * W + c.x2);
+  c.ax = __dsub_rn(x2d, px); c.bx = __dsub_rn(px, x1d); c.ay = __dsub_rn(y2d, py); c.by = __dsub_rn(py, y1d);
+  const double wa = __dmul_rn(c.ax, c.ay), wb = __dmul_rn(c.bx, c.ay), wc = __dmul_rn(c.ax, c.by), wd = __dmul_rn(c.bx, c.by);
+  c.dist = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(wa, c.v11), __dmul_rn(wb, c.v21)), __dmul_rn(wc, c.v12)), __dmul_rn(wd, c.v22));
+  const double gx = c.ay * (c.v21 - c.v11) + c.by * (c.v22 - c.v12);
+  const double gy = c.ax * (c.v12 - c.v11) + c.bx * (c.v22 - c.v21);
+  c.hx = gx * inv_res;      // = -J_x
+  c.hy = -gy * inv_res;     // = -J_y
+  return c;
+}
+
+template <int DOF>
+struct NodeGrad {
+  static constexpr int D = 2 * DOF;
+  double g_th[D];        // dL/d th_t (all contributions of the factors touching state t)
+  double g_prior[D];     // dL/d start (t == 0) or dL/d goal (t == T-1)
+  double g_q[D][D];      // dL/d Q_t^-1 (GP factor t, t < T-1)
+  double g_w, g_eps;     // dL/d w_t, dL/d eps_t
+};
+
+// Gradient contributions evaluated by the thread of state t.  lam*/dth* = lambda and dtheta of states
+// t-1, t, t+1 (ignored where they do not exist).  ghat = dL/d err_ext / M.  If g_sdf != nullptr the
+// SDF-tap gradients are accumulated there with atomics.
+template <int DOF, typename IO>
+__device__ __forceinline__ void backward_node(const KParams& P, const KWeights<IO>& Wt, int b, int t,
+                                              const double (&thp)[2 * DOF], const double (&th)[2 * DOF], const double (&thn)[2 * DOF],
+                                              const double (&lamp)[2 * DOF], const double (&lam)[2 * DOF], const double (&lamn)[2 * DOF],
+                                              const double (&dtp)[2 * DOF], const double (&dt)[2 * DOF], const double (&dtn)[2 * DOF],
+                                              const IO* __restrict__ start_b, const IO* __restrict__ goal_b,
+                                              const IO* __restrict__ sdf_b, double ghat, IO* __restrict__ g_sdf_b,
+                                              NodeGrad<DOF>& o) {
+  constexpr int D = 2 * DOF;
+  const int T = P.T;
+#pragma unroll
+  for (int a = 0; a < D; ++a) {
+    o.g_th[a] = 0.0; o.g_prior[a] = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) o.g_q[a][c] = 0.0;
+  }
+  o.g_w = 0.0; o.g_eps = 0.0;
+
+  // ---- priors: e = mean - th, H = I, K = k I ----
+  if (t == 0 || t == T - 1) {
+    const double k = (t == 0) ? P.ks : P.kg;
+    const IO* mean = (t == 0) ? start_b : goal_b;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      const double e = ldg_d(mean + a) - th[a];
+      const double alpha = k * lam[a] + ghat * k * e;
+      o.g_prior[a] = alpha;
+      o.g_th[a] -= alpha;
+    }
+  }
+  // ---- GP factor t (this state is the "Phi" side) ----
+  if (t < T - 1) {
+    double Q[D][D], g[D], a[D], rho[D], u[D];
+    load_qinv<DOF, IO>(P, Wt, b, t, Q);
+    gp_residual<DOF>(th, thn, P.dt, g);
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) {
+      a[i] = lam[i] + P.dt * lam[i + DOF] - lamn[i];                 // Phi lam_t - lam_{t+1}
+      a[i + DOF] = lam[i + DOF] - lamn[i + DOF];
+      u[i] = dt[i] + P.dt * dt[i + DOF] - dtn[i];                     // H dtheta = Phi dth_t - dth_{t+1}
+      u[i + DOF] = dt[i + DOF] - dtn[i + DOF];
+      rho[i] = g[i] - u[i];
+      rho[i + DOF] = g[i + DOF] - u[i + DOF];
+    }
+    double Qf[D][D];
+    fixed_qinv<DOF>(P, Qf);
+    double alpha[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double s = 0.0, sf = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        s += Q[i][c] * a[c];
+        sf += Qf[i][c] * g[c];
+        // dL/dK = a e^T - sym(a u^T): the reference's Cholesky backward symmetrises dL/dLambda, which only
+        // matters for a non-symmetric perturbation of K (the antisymmetric half of a u^T)
+        o.g_q[i][c] = a[i] * rho[c] + 0.5 * (a[i] * u[c] - u[i] * a[c]);
+      }
+      alpha[i] = s + ghat * sf;
+    }
+    // de = d th_{t+1} - Phi d th_t : this thread owns the -Phi^T alpha part
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) {
+      o.g_th[i] -= alpha[i];
+      o.g_th[i + DOF] -= P.dt * alpha[i] + alpha[i + DOF];
+    }
+  }
+  // ---- GP factor t-1 (this state is the "-I" side): + alpha_{t-1} ----
+  if (t > 0) {
+    double Q[D][D], g[D], a[D];
+    load_qinv<DOF, IO>(P, Wt, b, t - 1, Q);
+    gp_residual<DOF>(thp, th, P.dt, g);
+#pragma unroll
+    for (int i = 0; i < DOF; ++i) {
+      a[i] = lamp[i] + P.dt * lamp[i + DOF] - lam[i];
+      a[i + DOF] = lamp[i + DOF] - lam[i + DOF];
+    }
+    double Qf[D][D];
+    fixed_qinv<DOF>(P, Qf);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double s = 0.0, sf = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) { s += Q[i][c] * a[c]; sf += Qf[i][c] * g[c]; }
+      o.g_th[i] += s + ghat * sf;
+    }
+  }
+  // ---- obstacle factor ----
+  {
+    const double eps = (Wt.eps != nullptr) ? ldg_d(Wt.eps + (long long)b * Wt.e_sb + (long long)t * Wt.e_st) : P.eps_const;
+    const double w = (Wt.w != nullptr) ? ldg_d(Wt.w + (long long)b * Wt.w_sb + (long long)t * Wt.w_st) : P.w_const;
+    const double eps_tot = __dadd_rn(eps, P.r_sphere);
+    const SdfCell c = sdf_cell<IO>(sdf_b, P.H, P.W, P.orig_x, P.orig_y, P.res, P.inv_res, th[0], th[1]);
+    if (c.dist <= eps_tot) {
+      const double cost = eps_tot - c.dist;
+      const double a = c.hx * lam[0] + c.hy * lam[1];
+      const double rho = cost - (c.hx * dt[0] + c.hy * dt[1]);
+      const double alpha = w * a, beta = w * rho;
+      const double alpha_tot = alpha + ghat * P.w_fix * cost;
+      const double mx = beta * lam[0] - alpha * dt[0], my = beta * lam[1] - alpha * dt[1];
+      const double kap = (c.v22 - c.v12 - c.v21 + c.v11) * P.inv_res * P.inv_res;   // -d hx/dy = -d hy/dx
+      o.g_w = a * rho;
+      o.g_eps = alpha_tot;
+      o.g_th[0] += -alpha_tot * c.hx - my * kap;
+      o.g_th[1] += -alpha_tot * c.hy - mx * kap;
+      if (g_sdf_b != nullptr) {
+        const double ir = P.inv_res;
+        const double g11 = -alpha_tot * (c.ax * c.ay) - mx * c.ay * ir + my * c.ax * ir;
+        const double g21 = -alpha_tot * (c.bx * c.ay) + mx * c.ay * ir + my * c.bx * ir;
+        const double g12 = -alpha_tot * (c.ax * c.by) - mx * c.by * ir - my * c.ax * ir;
+        const double g22 = -alpha_tot * (c.bx * c.by) + mx * c.by * ir - my * c.bx * ir;
+        atomicAdd(g_sdf_b + (long long)c.y1 * P.W + c.x1, (IO)g11);
+        atomicAdd(g_sdf_b + (long long)c.y1 * P.W + c.x2, (IO)g21);
+        atomicAdd(g_sdf_b + (long long)c.y2 * P.W + c.x1, (IO)g12);
+        atomicAdd(g_sdf_b + (long long)c.y2 * P.W + c.x2, (IO)g22);
+      }
+    }
+  }
+  // ---- custom unary factors ----
+  if constexpr (DOF == 3) {
+    if (P.flags & FLAG_NONHOLONOMIC) {
+      double sh, ch;
+      sincos(th[2], &sh, &ch);
+      const double vx = th[3], vy = th[4];
+      const double e = vy * ch - vx * sh;
+      const double n2 = -vy * sh + vx * ch;
+      const double a = n2 * lam[2] - sh * lam[3] + ch * lam[4];
+      const double rho = e - (n2 * dt[2] - sh * dt[3] + ch * dt[4]);
+      const double alpha = P.kd * a, beta = P.kd * rho, alpha_tot = alpha + ghat * P.kd * e;
+      const double m2 = beta * lam[2] - alpha * dt[2], m3 = beta * lam[3] - alpha * dt[3], m4 = beta * lam[4] - alpha * dt[4];
+      o.g_th[2] += alpha_tot * (-vy * sh - vx * ch) + m2 * (-vy * ch - vx * sh) - m3 * ch - m4 * sh;
+      o.g_th[3] += -alpha_tot * sh + m2 * ch;
+      o.g_th[4] += alpha_tot * ch - m2 * sh;
+    }
+  }
+  if constexpr (DOF == 2) {
+    if (P.flags & FLAG_VEL_LIMITS) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const double v = th[2 + k], lim = (k == 0) ? P.vx_lim : P.vy_lim;
+        if (fabs(v) >= lim) {
+          const double sg = (double)((v > 0.0) - (v < 0.0));
+          const double cst = fabs(v) - lim;
+          const double a = -sg * lam[2 + k];
+          const double alpha_tot = P.kv * a + ghat * P.kv * cst;
+          o.g_th[2 + k] += alpha_tot * sg;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace dgpmp2

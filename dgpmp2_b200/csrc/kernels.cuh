@@ -25,26 +25,29 @@ struct StepSmem {
   double* nodes;    // [NP*T] records of Node<D>::kStride doubles
   double* nrm;      // [NP*T] per-node |dth|^2 (solve kernel only)
   IO* th;           // [NP*T][D] staged trajectory, natural (problem, t, a) order
+  IO* dth;          // [NP*T][D] staged forward step (backward kernel only)
   int* lvl_off;     // [kMaxLevels + 2]
   int* fail;        // [NP]
   int* flags;       // [2*NP] solve kernel: converged flag per problem, then iteration count
-  __host__ __device__ static size_t bytes(int NP, int T, bool solve) {
+  // mode: 0 = step, 1 = solve (adds nrm), 2 = backward (adds the dth stage)
+  __host__ __device__ static size_t bytes(int NP, int T, int mode) {
     const size_t NN = (size_t)NP * T;
     size_t b = NN * Node<D>::kStride * 8;
-    if (solve) b += NN * 8;
-    b += NN * D * sizeof(IO);
+    if (mode == 1) b += NN * 8;
+    b += NN * D * sizeof(IO) * (mode == 2 ? 2 : 1);
     b = (b + 15) & ~(size_t)15;
     b += (kMaxLevels + 2) * 4 + (size_t)NP * 4 * 3 + 16;
     return b;
   }
-  __device__ __forceinline__ void carve(unsigned char* raw, int NP, int T, bool solve) {
+  __device__ __forceinline__ void carve(unsigned char* raw, int NP, int T, int mode) {
     const size_t NN = (size_t)NP * T;
     nodes = reinterpret_cast<double*>(raw);
     double* nxt = nodes + NN * Node<D>::kStride;
     nrm = nxt;
-    if (solve) nxt += NN;
+    if (mode == 1) nxt += NN;
     th = reinterpret_cast<IO*>(nxt);
-    size_t off = (reinterpret_cast<unsigned char*>(th + NN * D) - raw + 15) & ~(size_t)15;
+    dth = th + NN * D;
+    size_t off = (reinterpret_cast<unsigned char*>(th + NN * D * (mode == 2 ? 2 : 1)) - raw + 15) & ~(size_t)15;
     lvl_off = reinterpret_cast<int*>(raw + off);
     fail = lvl_off + (kMaxLevels + 2);
     flags = fail + NP;
@@ -134,7 +137,7 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StepSmem<D, IO> S;
   const int T = P.T;
-  S.carve(smem_raw, NP, T, false);
+  S.carve(smem_raw, NP, T, 0);
   const int b0 = blockIdx.x * NP;
   const int np = min(NP, P.B - b0);
   DGPMP2_STAMP(0);
@@ -184,7 +187,7 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StepSmem<D, IO> S;
   const int T = P.T;
-  S.carve(smem_raw, NP, T, true);
+  S.carve(smem_raw, NP, T, 1);
   int* done = S.flags;          // [NP]
   int* nit = S.flags + NP;      // [NP]
   const int b0 = blockIdx.x * NP;
@@ -256,6 +259,112 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
   for (int p = threadIdx.x; p < np; p += blockDim.x) {
     iters[b0 + p] = nit[p];
     if (status != nullptr) status[b0 + p] = S.fail[p];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Backward of one GN step: lambda = Lambda^-1 gbar with the same assembly + BCR, then the factor VJPs.
+// Replaces autograd through the reference's dense solve (plan_layer.py:214-234).
+// ---------------------------------------------------------------------------
+template <int DOF, typename IO>
+__global__ void __launch_bounds__(DOF == 2 ? 512 : 256)
+gn_step_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th, const IO* __restrict__ start,
+                   const IO* __restrict__ goal, const IO* __restrict__ sdf, const IO* __restrict__ dth,
+                   const IO* __restrict__ g_dth, const IO* __restrict__ g_err_ext,
+                   IO* __restrict__ g_th, IO* __restrict__ g_start, IO* __restrict__ g_goal, IO* __restrict__ g_qc,
+                   IO* __restrict__ g_w, IO* __restrict__ g_eps, IO* __restrict__ g_sdf, const long long g_sdf_sb,
+                   const int NP) {
+  constexpr int D = 2 * DOF;
+  using N = Node<D>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  StepSmem<D, IO> S;
+  const int T = P.T;
+  S.carve(smem_raw, NP, T, 2);
+  const int b0 = blockIdx.x * NP;
+  const int np = min(NP, P.B - b0);
+
+  cta_prologue<D, IO>(P, S, T, NP, np, th + (size_t)b0 * T * D, false);
+  {
+    const IO* src = dth + (size_t)b0 * T * D;
+    const int n = np * T * D;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) S.dth[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int nlev = P.nlev;
+
+  assemble_cta<DOF, IO>(P, Wt, S, b0, np, nlev, start, goal, sdf);
+  __syncthreads();
+  {  // right-hand side := gbar (slot order)
+    const float inv_T = 1.0f / (float)T;
+    for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
+      const int p = fast_div(m, inv_T), slot = m - p * T;
+      const int t = bcr_state_of_slot(S.lvl_off, nlev, T, slot);
+      const IO* gp = g_dth + ((size_t)(b0 + p) * T + t) * D;
+      double v[D];
+#pragma unroll
+      for (int a = 0; a < D; ++a) v[a] = ldg_d(gp + a);
+      st_vec<D>(S.nodes + (size_t)m * N::kStride + N::oR, v);
+    }
+  }
+  __syncthreads();
+
+  bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, S.fail);   // lambda in every record's [oR, oR+D)
+
+  const double invM = 1.0 / (double)P.M;
+  const float inv_T = 1.0f / (float)T;
+  const int blk = (P.flags & FLAG_Q_FULL) ? D : DOF;
+  for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
+    const int p = fast_div(m, inv_T), t = m - p * T;
+    const int b = b0 + p;
+    double thp[D], thc[D], thn[D], lp[D], lc[D], ln[D], dp[D], dc[D], dn[D];
+    const IO* tp = S.th + ((size_t)p * T + t) * D;
+    const IO* xp = S.dth + ((size_t)p * T + t) * D;
+    const double* nb = S.nodes + (size_t)p * T * N::kStride;
+    ld_vec<D>(nb + (size_t)bcr_slot(S.lvl_off, T, t) * N::kStride + N::oR, lc);
+    if (t > 0) ld_vec<D>(nb + (size_t)bcr_slot(S.lvl_off, T, t - 1) * N::kStride + N::oR, lp);
+    if (t < T - 1) ld_vec<D>(nb + (size_t)bcr_slot(S.lvl_off, T, t + 1) * N::kStride + N::oR, ln);
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      thc[a] = (double)tp[a]; dc[a] = (double)xp[a];
+      thp[a] = (t > 0) ? (double)tp[a - D] : 0.0;      dp[a] = (t > 0) ? (double)xp[a - D] : 0.0;
+      thn[a] = (t < T - 1) ? (double)tp[a + D] : 0.0;  dn[a] = (t < T - 1) ? (double)xp[a + D] : 0.0;
+      if (t == 0) lp[a] = 0.0;
+      if (t == T - 1) ln[a] = 0.0;
+    }
+    const double ghat = (g_err_ext != nullptr) ? ldg_d(g_err_ext + b) * invM : 0.0;
+    NodeGrad<DOF> o;
+    backward_node<DOF, IO>(P, Wt, b, t, thp, thc, thn, lp, lc, ln, dp, dc, dn, start + (size_t)b * D, goal + (size_t)b * D,
+                           sdf + (size_t)b * P.sdf_sb, ghat, (g_sdf != nullptr) ? g_sdf + (size_t)b * g_sdf_sb : nullptr, o);
+    if (g_th != nullptr) {
+#pragma unroll
+      for (int a = 0; a < D; ++a) g_th[((size_t)b * T + t) * D + a] = (IO)o.g_th[a];
+    }
+    if (t == 0 && g_start != nullptr) {
+#pragma unroll
+      for (int a = 0; a < D; ++a) g_start[(size_t)b * D + a] = (IO)o.g_prior[a];
+    }
+    if (t == T - 1 && g_goal != nullptr) {
+#pragma unroll
+      for (int a = 0; a < D; ++a) g_goal[(size_t)b * D + a] = (IO)o.g_prior[a];
+    }
+    if (g_w != nullptr) g_w[(size_t)b * T + t] = (IO)o.g_w;
+    if (g_eps != nullptr) g_eps[(size_t)b * T + t] = (IO)o.g_eps;
+    if (g_qc != nullptr && t < T - 1) {
+      IO* q = g_qc + ((size_t)b * (T - 1) + t) * blk * blk;
+      if (P.flags & FLAG_Q_FULL) {
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+          for (int c = 0; c < D; ++c) q[a * D + c] = (IO)o.g_q[a][c];
+      } else {
+        // Q = [[qa C, qb C],[qb C, qc C]]  =>  dL/dC = qa G11 + qb (G12 + G21) + qc G22
+#pragma unroll
+        for (int a = 0; a < DOF; ++a)
+#pragma unroll
+          for (int c = 0; c < DOF; ++c)
+            q[a * DOF + c] = (IO)(P.qa * o.g_q[a][c] + P.qb * (o.g_q[a][c + DOF] + o.g_q[a + DOF][c]) + P.qc * o.g_q[a + DOF][c + DOF]);
+      }
+    }
   }
 }
 

@@ -75,8 +75,11 @@ class DiffGPMP2Planner(nn.Module):
         pl.obs_factor.set_inv_cov(w)
         pl.obs_factor.set_eps(eps)
         pl._state = dict(start=startb, goal=goalb, qc=qc, w=w, eps=eps, static=True)
-        if plan_time != float('inf'):
-            return self._forward_timed(th_initb, startb, goalb, imb, sdfb, plan_time, start_t)
+        needs_grad = torch.is_grad_enabled() and any(
+            isinstance(t, torch.Tensor) and t.requires_grad for t in (th_initb, startb, goalb, sdfb))
+        if plan_time != float('inf') or needs_grad:
+            # differentiable (unrolled, like the reference) or wall-clock-budgeted: batched step() loop
+            return self._forward_timed(th_initb, startb, goalb, imb, sdfb, plan_time, start_t, needs_grad)
         dt = work_dtype(th_initb, sdfb)
         out = ops.gn_solve(pl.cparams(), to_cuda(th_initb, dt), to_cuda(startb, dt), to_cuda(goalb, dt),
                            to_cuda(sdfb, dt), max_iters, tol_delta)
@@ -91,20 +94,21 @@ class DiffGPMP2Planner(nn.Module):
         return (back(th_final, th_initb).to(th_initb.dtype), None, err_initb, ef_h, err_per_iterb, err_ext_per_iterb,
                 iters_h, [elapsed] * B)
 
-    def _forward_timed(self, th_initb, startb, goalb, imb, sdfb, plan_time, start_t):
-        """Wall-clock-budgeted variant (optim_params['plan_time'] finite): batched step() loop with
-        per-problem convergence masks and the reference's budget check (:154-156)."""
+    def _forward_timed(self, th_initb, startb, goalb, imb, sdfb, plan_time, start_t, needs_grad=False):
+        """Batched step() loop with per-problem convergence masks: used when the result must be
+        differentiable (the unrolled iterations stay on the autograd tape, as in the reference) or when
+        optim_params['plan_time'] is finite (the reference's budget check, :154-156)."""
         B = th_initb.shape[0]
         max_iters = int(self.optim_params['max_iters'])
         tol_delta = as_float(self.optim_params['tol_delta'])
-        th = th_initb.detach().clone()
+        th = th_initb if needs_grad else th_initb.detach().clone()
         done = torch.zeros(B, dtype=torch.bool, device=th.device)
         iters = [0] * B
         epi = [[] for _ in range(B)]
         eepi = [[] for _ in range(B)]
         for j in range(max_iters):
             dth, _, err, err_ext, _, _, _ = self.step(th, startb, goalb, imb, sdfb)
-            nrm = torch.norm(dth.reshape(B, -1), dim=1)
+            nrm = torch.norm(dth.detach().reshape(B, -1), dim=1)
             e_h, ee_h, nrm_h, done_h = err.reshape(-1).tolist(), err_ext.reshape(-1).tolist(), nrm.tolist(), done.tolist()
             for i in range(B):
                 if not done_h[i]:
@@ -115,10 +119,10 @@ class DiffGPMP2Planner(nn.Module):
             done = done | (nrm < tol_delta)
             if bool(done.all()):
                 break
-            if time.time() - start_t > plan_time:
+            if plan_time != float('inf') and time.time() - start_t > plan_time:
                 print('Plan time over')
                 break
-        ef = self.plan_layer.error_batch(th, sdfb).reshape(-1).tolist()
+        ef = self.plan_layer.error_batch(th.detach(), sdfb.detach()).reshape(-1).tolist()
         return (th, None, [e[0] for e in epi], ef, epi, eepi, iters, [time.time() - start_t] * B)
 
     # ------------------------------------------------------------------ one iteration

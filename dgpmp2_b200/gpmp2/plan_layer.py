@@ -24,6 +24,52 @@ from .gp import GPFactor, PriorFactor
 from .obstacle import ObstacleFactor
 
 
+class _GNStep(torch.autograd.Function):
+    """dtheta, err, err_ext = GN step, differentiable w.r.t. th, start, goal, sdf, qc_inv, obscov_inv, eps.
+    Forward: dgpmp2_gn_step_*; backward: dgpmp2_gn_step_backward_* (adjoint solve with the same block
+    cyclic reduction + factor VJPs).  err is not differentiable (the reference computes it under no_grad)."""
+
+    @staticmethod
+    def forward(ctx, layer, static, th, start, goal, sdf, qc, w, eps):
+        dt = work_dtype(th, sdf)
+        p = layer.cparams()
+        c = lambda t: to_cuda(t, dt)
+        thc, stc, goc, sdfc = c(th), c(start), c(goal), c(sdf)
+        kw = {} if static else dict(qc_inv=c(qc), w_obs=c(w), eps=c(eps))
+        dth, err, err_ext, status = ops.gn_step(p, thc, stc, goc, sdfc, want_status=True, **kw)
+        layer._check(status)
+        ctx.layer, ctx.static, ctx.dt = layer, static, dt
+        ctx.meta = [(t.device, t.dtype, tuple(t.shape)) if isinstance(t, torch.Tensor) else None for t in (th, start, goal, sdf, qc, w, eps)]
+        ctx.save_for_backward(thc, stc, goc, sdfc, dth, *([] if static else [kw['qc_inv'], kw['w_obs'], kw['eps']]))
+        B = th.shape[0]
+        out = (back(dth, th).to(th.dtype), back(err, th).to(th.dtype).reshape(B, 1, 1), back(err_ext, th).to(th.dtype).reshape(B, 1, 1))
+        ctx.mark_non_differentiable(out[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, g_dth, g_err, g_err_ext):
+        layer, static, dt = ctx.layer, ctx.static, ctx.dt
+        saved = ctx.saved_tensors
+        thc, stc, goc, sdfc, dth = saved[:5]
+        kw = {} if static else dict(qc_inv=saved[5], w_obs=saved[6], eps=saved[7])
+        need = ctx.needs_input_grad          # (layer, static, th, start, goal, sdf, qc, w, eps)
+        B = thc.shape[0]
+        gd = to_cuda(g_dth, dt) if g_dth is not None else torch.zeros_like(dth)
+        ge = to_cuda(g_err_ext, dt).reshape(B) if g_err_ext is not None else None
+        outs = ops.gn_step_backward(layer.cparams(), thc, stc, goc, sdfc, dth, gd, ge,
+                                    need_th=need[2], need_start=need[3], need_goal=need[4], need_sdf=need[5],
+                                    need_qc=need[6] and not static, need_w=need[7] and not static,
+                                    need_eps=need[8] and not static, **kw)
+        g_th, g_start, g_goal, g_qc, g_w, g_eps, g_sdf = outs
+
+        def fit(g, k):
+            if g is None or ctx.meta[k] is None:
+                return None
+            dev, dtype, shape = ctx.meta[k]
+            return g.reshape(shape).to(device=dev, dtype=dtype)
+        return (None, None, fit(g_th, 0), fit(g_start, 1), fit(g_goal, 2), fit(g_sdf, 3), fit(g_qc, 4), fit(g_w, 5), fit(g_eps, 6))
+
+
 class PlanLayer(nn.Module):
     def __init__(self, gp_params, obs_params, planner_params, optim_params, env_params, robot_model,
                  learn_params=None, batch_size=1, use_cuda=False):
@@ -124,20 +170,8 @@ class PlanLayer(nn.Module):
         self.obs_factor.set_eps(eps_trajb)
         static = self._is_static(qc_inv_trajb, obscov_inv_trajb, eps_trajb)
         self._state = dict(start=startb, goal=goalb, qc=qc_inv_trajb, w=obscov_inv_trajb, eps=eps_trajb, static=static)
-        dt = work_dtype(thb, sdfb)
-        B = thb.shape[0]
-        th, st, go, sdf = to_cuda(thb, dt), to_cuda(startb, dt), to_cuda(goalb, dt), to_cuda(sdfb, dt)
-        p = self.cparams()
-        if static:
-            dth, err, err_ext, status = ops.gn_step(p, th, st, go, sdf, want_status=True)
-        else:
-            dth, err, err_ext, status = ops.gn_step(p, th, st, go, sdf, qc_inv=to_cuda(qc_inv_trajb, dt),
-                                                    w_obs=to_cuda(obscov_inv_trajb, dt), eps=to_cuda(eps_trajb, dt),
-                                                    want_status=True)
-        self._check(status)
-        out_dt = thb.dtype
-        return (back(dth, thb).to(out_dt), back(err, thb).to(out_dt).reshape(B, 1, 1),
-                back(err_ext, thb).to(out_dt).reshape(B, 1, 1))
+        # expanded (broadcast) weight tensors are passed as they are; autograd sums their gradient
+        return _GNStep.apply(self, static, thb, startb, goalb, sdfb, qc_inv_trajb, obscov_inv_trajb, eps_trajb)
 
     def _check(self, status):
         self.last_status = status

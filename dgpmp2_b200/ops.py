@@ -80,6 +80,32 @@ def gn_step(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None,
     return dth, err, err_ext, status
 
 
+def gn_step_backward(p: CParams, th, start, goal, sdf, dth, g_dth, g_err_ext=None, qc_inv=None, w_obs=None, eps=None,
+                     need_th=True, need_start=False, need_goal=False, need_qc=False, need_w=False, need_eps=False,
+                     need_sdf=False):
+    """Backward of gn_step: returns (g_th, g_start, g_goal, g_qc, g_w, g_eps, g_sdf); entries not asked for are None.
+    g_qc is dense (B,T-1,blk,blk), g_w / g_eps are (B,T), g_sdf has the layout of the (contiguous) sdf."""
+    th, start, goal, sdf = _common(p, th, start, goal, sdf)
+    B, T, d = th.shape
+    dt, dev = th.dtype, th.device
+    dth = _prep(dth, dt, 'dth')
+    g_dth = _prep(g_dth, dt, 'g_dth')
+    g_ee = _prep(g_err_ext.reshape(B), dt, 'g_err_ext') if g_err_ext is not None else None
+    blk = 2 * p.dof if (p.flags & _lib.FLAG_Q_FULL) else p.dof
+    g_th = torch.empty_like(th) if need_th else None
+    g_start = torch.empty(B, d, dtype=dt, device=dev) if need_start else None
+    g_goal = torch.empty(B, d, dtype=dt, device=dev) if need_goal else None
+    g_qc = torch.empty(B, T - 1, blk, blk, dtype=dt, device=dev) if need_qc else None
+    g_w = torch.empty(B, T, dtype=dt, device=dev) if need_w else None
+    g_eps = torch.empty(B, T, dtype=dt, device=dev) if need_eps else None
+    g_sdf = torch.zeros_like(sdf) if need_sdf else None          # accumulated with atomics
+    wref, keep = _weights(p, dt, qc_inv, w_obs, eps, B, T)
+    fn = getattr(load(), 'dgpmp2_gn_step_backward_' + suffix(dt))
+    check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(sdf), wref, ptr(dth), ptr(g_dth), ptr(g_ee),
+             ptr(g_th), ptr(g_start), ptr(g_goal), ptr(g_qc), ptr(g_w), ptr(g_eps), ptr(g_sdf), stream_ptr()))
+    return g_th, g_start, g_goal, g_qc, g_w, g_eps, g_sdf
+
+
 def gn_solve(p: CParams, th, start, goal, sdf, max_iters: int, tol_delta: float, qc_inv=None, w_obs=None, eps=None):
     """Persistent solve to convergence. Returns th_final, iters, err_per_iter (B,max_iters; NaN beyond iters),
     err_ext_per_iter, err_final, err_ext_final, status."""

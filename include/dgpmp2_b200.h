@@ -111,6 +111,29 @@ int dgpmp2_gn_step_f64(const dgpmp2_params* p, const double* th, const double* s
                        double* dth, double* err, double* err_ext, int32_t* status, void* stream);
 
 /*
+ * Backward (reverse-mode derivative) of dgpmp2_gn_step_* -- replaces autograd through the
+ * reference's dense A/b/K scatter, normal equations, Cholesky and inverses (plan_layer.py:152-234),
+ * which is what makes the planner "differentiable" (learning/train_planner.py:366-374,
+ * examples/diff_gpmp2_2d_example.py:75-78).  Recomputes the band from the inputs, solves
+ * lambda = Lambda^-1 g_dth with the same block cyclic reduction and evaluates the factor VJPs.
+ *   inputs : the forward inputs, dth = forward output (B,T,d), g_dth = dL/d dth (B,T,d),
+ *            g_err_ext = dL/d err_ext (B) or NULL (err itself is not differentiable in the
+ *            reference: it is computed under torch.no_grad, plan_layer.py:275)
+ *   outputs (any may be NULL): g_th (B,T,d), g_start (B,d), g_goal (B,d),
+ *            g_qc (B,T-1,dof,dof) -- or (B,T-1,d,d) with DGPMP2_FLAG_Q_FULL -- dense per-(b,t),
+ *            g_w (B,T), g_eps (B,T),
+ *            g_sdf (same layout as sdf; ACCUMULATED with atomics, the caller zero-fills it).
+ */
+int dgpmp2_gn_step_backward_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal,
+                                const float* sdf, const dgpmp2_weights* w, const float* dth, const float* g_dth,
+                                const float* g_err_ext, float* g_th, float* g_start, float* g_goal, float* g_qc,
+                                float* g_w, float* g_eps, float* g_sdf, void* stream);
+int dgpmp2_gn_step_backward_f64(const dgpmp2_params* p, const double* th, const double* start, const double* goal,
+                                const double* sdf, const dgpmp2_weights* w, const double* dth, const double* g_dth,
+                                const double* g_err_ext, double* g_th, double* g_start, double* g_goal, double* g_qc,
+                                double* g_w, double* g_eps, double* g_sdf, void* stream);
+
+/*
  * Optimise to convergence in ONE persistent launch -- replaces the per-sample
  * loop of DiffGPMP2Planner.forward (diff_gpmp2_planner.py:104-165) with static
  * or per-call-constant weights: per problem, th <- th + dth until

@@ -216,6 +216,32 @@ def main():
                         dist=dist.numpy(), J=J.numpy())
     print('bilinear: zero-dist points (outside) = %d / %d' % (int((dist == 0).sum()), dist.numel()))
 
+    # 9. gradients of one GN step through the reference's own autograd graph (dense scatter + cholesky + inverse)
+    B, T = 2, 16
+    th, s_, g_, sdf = synth(B, T, 64, seed=11)
+    th = th + 0.05 * torch.as_tensor(rng.standard_normal(th.shape))
+    q = torch.as_tensor(rng.standard_normal((B, T - 1, 2, 1)))
+    qc = q @ q.transpose(2, 3) + torch.eye(2) * torch.as_tensor(rng.uniform(0.2, 1.5, (B, T - 1, 1, 1)))
+    w = torch.as_tensor(rng.uniform(50.0, 2.0e4, (B, T, 1, 1)))
+    eps = torch.as_tensor(rng.uniform(0.3, 1.2, (B, T, 1, 1)))
+    leaves = [r32(x).requires_grad_(True) for x in (th, s_, g_, sdf, qc, w, eps)]
+    planner = ref_harness.make_reference_planner(B, T, YAML, lims, lims)
+    dth, err, err_ext = planner.plan_layer(leaves[0], leaves[1], leaves[2], torch.zeros_like(leaves[3]), leaves[3],
+                                           leaves[4], leaves[5], leaves[6])
+    G = torch.as_tensor(rng.standard_normal(dth.shape))
+    g2 = torch.as_tensor(rng.standard_normal(err_ext.shape))
+    loss = (dth * G).sum() + (err_ext * g2).sum()
+    grads = torch.autograd.grad(loss, leaves, allow_unused=True)
+    names = ['th', 'start', 'goal', 'sdf', 'qc', 'w', 'eps']
+    out = {n: l.detach().numpy().astype(np.float32) for n, l in zip(names, leaves)}
+    out.update({'g_' + n: (gr.numpy() if gr is not None else np.zeros(tuple(l.shape))) for n, gr, l in zip(names, grads, leaves)})
+    out.update(G=G.numpy(), g_err_ext=g2.numpy(), dth=dth.detach().numpy(), err_ext=err_ext.detach().numpy(), T=T,
+               x_lims=np.array(lims), y_lims=np.array(lims), err_requires_grad=bool(err.requires_grad))
+    np.savez_compressed(os.path.join(OUT, 'grad_B2_T16.npz'), **out)
+    print('grad_B2_T16: |g_th|max=%.3e |g_sdf|max=%.3e |g_qc|max=%.3e |g_w|max=%.3e |g_eps|max=%.3e err.requires_grad=%s' % (
+        float(grads[0].abs().max()), float(grads[3].abs().max()), float(grads[4].abs().max()), float(grads[5].abs().max()),
+        float(grads[6].abs().max()), err.requires_grad))
+
     # 8. nonholonomic factor on one (T,6) trajectory (the only way the reference can run it)
     from diff_gpmp2.gpmp2.custom_factors import NonHolonomicFactor
     T = 12
