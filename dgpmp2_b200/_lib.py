@@ -66,6 +66,8 @@ PROTOTYPES = {
     'dgpmp2_factors_f64': [_P(CParams), _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp, _vp],
     'dgpmp2_sdf_lookup_f32': [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _f64, _f64, _f64, _vp, _vp, _vp],
     'dgpmp2_sdf_lookup_f64': [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _f64, _f64, _f64, _vp, _vp, _vp],
+    'dgpmp2_sdf_from_occupancy_f32': [_vp, _i32, _i32, _i32, _i32, _f64, _f64, _vp, _vp],
+    'dgpmp2_sdf_from_occupancy_f64': [_vp, _i32, _i32, _i32, _i32, _f64, _f64, _vp, _vp],
     'dgpmp2_band_f32': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp],
     'dgpmp2_band_f64': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp],
     'dgpmp2_host_step_workspace_bytes': [_P(CParams), _i32, _P(_sz)],

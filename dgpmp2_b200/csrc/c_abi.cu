@@ -366,6 +366,23 @@ int sdf_lookup_impl(const IO* sdf, int32_t B, int32_t H, int32_t W, int64_t sdf_
   return DGPMP2_OK;
 }
 
+template <typename IO>
+int sdf_from_occupancy_impl(const IO* im, int32_t B, int32_t H, int32_t W, int32_t pad, double thresh, double res, IO* out,
+                            void* stream) {
+  if (B < 0 || H < 1 || W < 1 || pad < 0 || !(res > 0.0)) return DGPMP2_ERR_ARG;
+  if (B == 0) return DGPMP2_OK;
+  if (!im || !out) return DGPMP2_ERR_ARG;
+  const size_t Hp = (size_t)H + 2 * pad, Wp = (size_t)W + 2 * pad;
+  const size_t bytes = Hp * Wp * 2 * sizeof(unsigned short);
+  if (bytes > (size_t)kSmemLimit || Hp >= 65535 || Wp >= 65535) return DGPMP2_ERR_UNSUPPORTED;
+  auto kern = sdf_from_occupancy_kernel<IO>;
+  int rc = allow_smem(kern, (int)bytes);
+  if (rc != DGPMP2_OK) return rc;
+  kern<<<B, 256, bytes, static_cast<cudaStream_t>(stream)>>>(im, H, W, pad, thresh, res, out);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
+}
+
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct HostWs { size_t th, start, goal, sdf, dth, err, err_ext, status, total; };
@@ -512,6 +529,15 @@ int dgpmp2_sdf_lookup_f32(const float* sdf, int32_t B, int32_t H, int32_t W, int
 int dgpmp2_sdf_lookup_f64(const double* sdf, int32_t B, int32_t H, int32_t W, int64_t sdf_stride_b, const double* pts,
                           int32_t N, double res, double x_lo, double y_lo, double* dist, double* J, void* stream) {
   return sdf_lookup_impl<double>(sdf, B, H, W, sdf_stride_b, pts, N, res, x_lo, y_lo, dist, J, stream);
+}
+
+int dgpmp2_sdf_from_occupancy_f32(const float* im, int32_t B, int32_t H, int32_t W, int32_t padlen, double thresh,
+                                  double res, float* sdf_out, void* stream) {
+  return sdf_from_occupancy_impl<float>(im, B, H, W, padlen, thresh, res, sdf_out, stream);
+}
+int dgpmp2_sdf_from_occupancy_f64(const double* im, int32_t B, int32_t H, int32_t W, int32_t padlen, double thresh,
+                                  double res, double* sdf_out, void* stream) {
+  return sdf_from_occupancy_impl<double>(im, B, H, W, padlen, thresh, res, sdf_out, stream);
 }
 
 int dgpmp2_band_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal, const float* sdf,

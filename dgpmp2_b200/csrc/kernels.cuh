@@ -536,4 +536,67 @@ sdf_lookup_kernel(const IO* __restrict__ sdf, int B, int H, int W, long long sdf
   }
 }
 
+// ---------------------------------------------------------------------------
+// Signed Euclidean distance field of an occupancy image -- replaces sdf_2d (utils/sdf_utils.py:6-21,
+// datasets/utils.py:4-18), i.e. two scipy.ndimage.distance_transform_edt calls per map.
+// One CTA per image.  Pass 1: per column, distance to the nearest background pixel of that column
+// (both polarities at once).  Pass 2: per pixel, exact minimum over the row of dx^2 + g^2 in integer
+// arithmetic, then sqrt in double: bit-identical to the exact EDT.  scipy's behaviour for an image
+// WITHOUT any background pixel (distance to a virtual pixel at row -1, column 0) is reproduced.
+// ---------------------------------------------------------------------------
+template <typename IO>
+__global__ void __launch_bounds__(256)
+sdf_from_occupancy_kernel(const IO* __restrict__ im, int H, int W, int pad, double thresh, double res,
+                          IO* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  unsigned short* g0 = reinterpret_cast<unsigned short*>(smem_raw);   // distance in the column to the nearest OBSTACLE pixel
+  unsigned short* g1 = g0 + (size_t)Hp * Wp;                          // ... to the nearest FREE pixel
+  const IO* src = im + (size_t)blockIdx.x * H * W;
+  constexpr unsigned short INF = 65535;
+  int any_obst = 0, any_free = 0;
+  for (int x = threadIdx.x; x < Wp; x += blockDim.x) {
+    unsigned short d0 = INF, d1 = INF;
+    for (int y = 0; y < Hp; ++y) {                       // downward scan
+      const int yy = y - pad, xx = x - pad;
+      const bool inside = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const bool free_px = inside ? ((double)src[(size_t)yy * W + xx] > thresh) : true;   // padding is free space
+      d0 = free_px ? (d0 == INF ? INF : (unsigned short)(d0 + 1)) : 0;
+      d1 = free_px ? 0 : (d1 == INF ? INF : (unsigned short)(d1 + 1));
+      any_obst |= !free_px;
+      any_free |= free_px;
+      g0[(size_t)y * Wp + x] = d0;
+      g1[(size_t)y * Wp + x] = d1;
+    }
+    d0 = INF; d1 = INF;
+    for (int y = Hp - 1; y >= 0; --y) {                  // upward scan
+      const unsigned short a0 = g0[(size_t)y * Wp + x], a1 = g1[(size_t)y * Wp + x];
+      d0 = (a0 == 0) ? 0 : (d0 == INF ? INF : (unsigned short)(d0 + 1));
+      d1 = (a1 == 0) ? 0 : (d1 == INF ? INF : (unsigned short)(d1 + 1));
+      g0[(size_t)y * Wp + x] = min(a0, d0);
+      g1[(size_t)y * Wp + x] = min(a1, d1);
+    }
+  }
+  const int has_obst = __syncthreads_or(any_obst);
+  const int has_free = __syncthreads_or(any_free);
+  IO* dst = out + (size_t)blockIdx.x * Hp * Wp;
+  for (int i = threadIdx.x; i < Hp * Wp; i += blockDim.x) {
+    const int y = i / Wp, x = i - y * Wp;
+    long long b0 = -1, b1 = -1;
+    const unsigned short* r0 = g0 + (size_t)y * Wp;
+    const unsigned short* r1 = g1 + (size_t)y * Wp;
+    for (int xp = 0; xp < Wp; ++xp) {
+      const long long dx2 = (long long)(x - xp) * (x - xp);
+      const unsigned short a0 = r0[xp], a1 = r1[xp];
+      if (a0 != INF) { const long long c = dx2 + (long long)a0 * a0; b0 = (b0 < 0 || c < b0) ? c : b0; }
+      if (a1 != INF) { const long long c = dx2 + (long long)a1 * a1; b1 = (b1 < 0 || c < b1) ? c : b1; }
+    }
+    // no background pixel at all: scipy (1.18) measures from a virtual pixel at row -1, column 0
+    const double quirk = sqrt((double)((long long)(y + 1) * (y + 1) + (long long)x * x));
+    const double d_free = has_obst ? sqrt((double)b0) : quirk;      // EDT(im): free pixels -> nearest obstacle
+    const double d_obst = has_free ? sqrt((double)b1) : quirk;      // EDT(1 - im): obstacle pixels -> nearest free
+    dst[i] = (IO)((d_free - d_obst) * res);
+  }
+}
+
 }  // namespace dgpmp2

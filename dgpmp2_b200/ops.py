@@ -179,6 +179,20 @@ def sdf_lookup(sdf, pts, res: float, x_lo: float, y_lo: float):
     return dist, J
 
 
+def sdf_from_occupancy(im, padlen: int = 1, res: float = 1.0, thresh: float = 0.75):
+    """Batched signed distance field on the GPU: im (B,H,W) or (H,W) CUDA tensor -> (B,H+2p,W+2p), exact EDT."""
+    _lib.require_cuda()
+    if im.dim() == 2:
+        im = im.unsqueeze(0)
+    dt = im.dtype if im.dtype in (torch.float32, torch.float64) else torch.float32
+    im = _prep(im, dt, 'im')
+    B, H, W = im.shape
+    out = torch.empty(B, H + 2 * padlen, W + 2 * padlen, dtype=dt, device=im.device)
+    fn = getattr(load(), 'dgpmp2_sdf_from_occupancy_' + suffix(dt))
+    check(fn(ptr(im), B, H, W, int(padlen), float(thresh), float(res), ptr(out), stream_ptr()))
+    return out
+
+
 def band(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None):
     """Information band in float64: D (B,T,d,d), U (B,T-1,d,d), r (B,T,d)."""
     th, start, goal, sdf = _common(p, th, start, goal, sdf)

@@ -195,6 +195,20 @@ int dgpmp2_sdf_lookup_f64(const double* sdf, int32_t B, int32_t H, int32_t W, in
                           double* dist, double* J, void* stream);
 
 /*
+ * Signed distance field of a batch of occupancy images -- replaces sdf_2d (utils/sdf_utils.py:6-21,
+ * datasets/utils.py:4-18: free = image > 0.75, optional padding with free cells, two
+ * scipy.ndimage.distance_transform_edt calls, (edt(free) - edt(occupied)) * res).  Exact Euclidean
+ * distance transform (integer squared distances, sqrt in double), including scipy's behaviour for
+ * images without any background pixel.
+ *   im (B,H,W) -> sdf_out (B, H+2*padlen, W+2*padlen); positive in free space.
+ *   Limit: (H+2p)*(W+2p)*4 bytes of shared memory <= 227 KB (e.g. 238 x 238), else DGPMP2_ERR_UNSUPPORTED.
+ */
+int dgpmp2_sdf_from_occupancy_f32(const float* im, int32_t B, int32_t H, int32_t W, int32_t padlen, double thresh,
+                                  double res, float* sdf_out, void* stream);
+int dgpmp2_sdf_from_occupancy_f64(const double* im, int32_t B, int32_t H, int32_t W, int32_t padlen, double thresh,
+                                  double res, double* sdf_out, void* stream);
+
+/*
  * The block-tridiagonal information system itself (what the reference holds as
  * dense A^T K A + reg I and A^T K b, plan_layer.py:217-220), always in double:
  *   D (B,T,d,d) diagonal blocks, U (B,T-1,d,d) blocks (t,t+1), r (B,T,d).

@@ -193,3 +193,24 @@ def test_not_positive_definite_raises_like_the_reference():
     planner.plan_layer.strict = False              # opt out of the host sync: status stays on the device
     planner.step(th, z, z, None, sdf)
     assert int(planner.plan_layer.last_status.min()) > 0
+
+
+@pytest.mark.parametrize('H,W,pad', [(128, 128, 0), (200, 200, 1), (37, 61, 2), (16, 16, 0)])
+def test_gpu_sdf_generation_bit_exact_vs_scipy_sdf_2d(H, W, pad):
+    """Row (f3): sdf_2d on the GPU == the reference's scipy EDT path (exact EDT => bit-identical in fp64)."""
+    from diff_gpmp2.utils.sdf_utils import sdf_2d, sdf_2d_gpu
+    from dgpmp2_b200.datasets.synthetic import random_obstacle_map
+    rng = np.random.default_rng(H + W)
+    ims = [random_obstacle_map(rng, H, 'forest')[:H, :W] if H == W else (rng.random((H, W)) > 0.3).astype(np.float64) for _ in range(5)]
+    ims.append(np.ones((H, W)))            # no obstacle at all: scipy's virtual background pixel at (-1,-1)
+    ims.append(np.zeros((H, W)))           # fully occupied
+    one = np.ones((H, W)); one[H // 2, W // 3] = 0.0
+    ims.append(one)
+    res = 10.0 / W
+    got = sdf_2d_gpu(np.stack(ims), padlen=pad, res=res).cpu().numpy()
+    for k, im in enumerate(ims):
+        ref = sdf_2d(im, padlen=pad, res=res)
+        assert got[k].shape == ref.shape
+        np.testing.assert_array_equal(got[k], ref)
+    got32 = sdf_2d_gpu(torch.tensor(np.stack(ims), dtype=torch.float32), padlen=pad, res=res).cpu().numpy()
+    np.testing.assert_allclose(got32, got, rtol=1e-6, atol=1e-6)
