@@ -213,7 +213,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--steps', type=int, default=20000)
     ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--impl', type=str, default='b200')
     ap.add_argument('--e2e-steps', type=int, default=20)
