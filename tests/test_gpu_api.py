@@ -214,3 +214,20 @@ def test_gpu_sdf_generation_bit_exact_vs_scipy_sdf_2d(H, W, pad):
         np.testing.assert_array_equal(got[k], ref)
     got32 = sdf_2d_gpu(torch.tensor(np.stack(ims), dtype=torch.float32), padlen=pad, res=res).cpu().numpy()
     np.testing.assert_allclose(got32, got, rtol=1e-6, atol=1e-6)
+
+
+def test_headless_batch_example_runs_end_to_end():
+    """The reference's batch-example flow (YAML -> PlanningDataset/DataLoader -> straight lines -> planner.forward)
+    through the diff_gpmp2 import paths, on a dataset written in the reference's on-disk format."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'examples', 'diff_gpmp2_2d_batch_example_headless.py')
+    spec = importlib.util.spec_from_file_location('headless_example', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    try:
+        th_final, e0, e1, jb = mod.main(['--batch', '3', '--steps', '31'])
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert th_final.shape == (3, 32, 4) and th_final.device.type == 'cpu' and len(jb) == 3
+    assert all(b < a for a, b in zip(e0, e1))          # Gauss-Newton lowered the cost of every problem
