@@ -327,6 +327,12 @@ int factors_impl(const dgpmp2_params* p, const IO* th, const IO* sdf, const dgpm
   const KWeights<IO> kw = make_kweights<IO>(w);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int g = grid_for((long long)p->B * p->T, 256);
+  if (gp_err == nullptr && cust_err == nullptr && cust_H == nullptr) {   // obstacle factor only: streaming fast path
+    if (p->dof == 2) obstacle_kernel<2, IO><<<g, 256, 0, st>>>(k, kw, th, sdf, obs_cost, obs_H);
+    else obstacle_kernel<3, IO><<<g, 256, 0, st>>>(k, kw, th, sdf, obs_cost, obs_H);
+    CUDA_TRY(cudaGetLastError());
+    return DGPMP2_OK;
+  }
   if (p->dof == 2)
     factors_kernel<2, IO><<<g, 256, 0, st>>>(k, kw, th, sdf, gp_err, obs_cost, obs_H, cust_err, cust_H);
   else

@@ -520,6 +520,43 @@ factors_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
 }
 
 // ---------------------------------------------------------------------------
+// Obstacle factor alone (the streaming fast path of factors_kernel): fused SDF bilinear lookup +
+// hinge + Jacobian, one thread per state.  Reads only the 2-D position of each state (one vector
+// load), the four SDF taps through the read-only path, and writes cost and the d-wide Jacobian row
+// with vector stores.  HBM-bound at >= 1e6 states per launch (profiles/README.md).
+// ---------------------------------------------------------------------------
+template <typename IO> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+
+template <int DOF, typename IO>
+__global__ void __launch_bounds__(256)
+obstacle_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th, const IO* __restrict__ sdf,
+                IO* __restrict__ obs_cost, IO* __restrict__ obs_H) {
+  constexpr int D = 2 * DOF;
+  using V2 = typename Vec2<IO>::type;
+  const int T = P.T;
+  const long long n = (long long)P.B * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / T), t = (int)(i - (long long)b * T);
+    const V2 pos = __ldg(reinterpret_cast<const V2*>(th + (size_t)i * D));
+    const double eps = (Wt.eps != nullptr) ? ldg_d(Wt.eps + (long long)b * Wt.e_sb + (long long)t * Wt.e_st) : P.eps_const;
+    const SdfSample s = sdf_bilinear<IO, false>(sdf + (size_t)b * P.sdf_sb, P.H, P.W, P.orig_x, P.orig_y, P.res,
+                                                (double)pos.x, (double)pos.y, P.inv_res);
+    const ObsTerm ob = hinge(s, __dadd_rn(eps, P.r_sphere));
+    if (obs_cost != nullptr) obs_cost[i] = (IO)ob.c;
+    if (obs_H != nullptr) {
+      V2* h = reinterpret_cast<V2*>(obs_H + (size_t)i * D);
+      V2 h0; h0.x = (IO)ob.hx; h0.y = (IO)ob.hy;
+      V2 z; z.x = (IO)0; z.y = (IO)0;
+      h[0] = h0;
+#pragma unroll
+      for (int k = 1; k < DOF; ++k) h[k] = z;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // bilinear_interpolate (utils/sdf_utils.py:38-107)
 // ---------------------------------------------------------------------------
 template <typename IO>
