@@ -345,6 +345,49 @@ def main():
 
     e2e_val = e2e_run(False)
     e2e_res = e2e_run(True)
+
+    # ---------------- SURVEY 8(d) extras (device-resident, not the headline): iterate 0 / 10, persistent solve ----------------
+    def time_launches(fn_one, n):
+        for _ in range(3):
+            fn_one()
+        barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n):
+                fn_one()
+        g.replay()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        g.replay()
+        a1.record(stream)
+        barrier()
+        return a0.elapsed_time(a1) / n
+
+    extras = {}
+    pr0 = sets[0]
+    th0, st0, go0, sdf0 = (pr0[k].to(dev).contiguous() for k in ('th_init', 'start', 'goal', 'sdf'))
+    for k_it in (0, 10):
+        thk = th0 if k_it == 0 else ops.gn_solve(cp, th0, st0, go0, sdf0, k_it, 0.0)[0].contiguous()
+        a = (vp(thk.data_ptr()), vp(st0.reshape(B, d).data_ptr()), vp(go0.reshape(B, d).data_ptr()), vp(sdf0[:, 0].data_ptr()))
+
+        def one(a=a):
+            rc = fn(pref, a[0], a[1], a[2], a[3], None, outs[0], outs[1], outs[2], outs[3], vp(torch.cuda.current_stream().cuda_stream))
+            if rc != 0:
+                _lib.check(rc)
+        extras['step_iterate_%d_problem_iters_per_sec' % k_it] = B / (time_launches(one, 50) * 1e-3)
+    _lib.set_sdf_shape(cp, IM_SIZE, IM_SIZE, IM_SIZE * IM_SIZE)
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ops.gn_solve(cp, th0, st0, go0, sdf0, 100, 1e-4)
+    barrier()
+    a0.record(stream)
+    sol = ops.gn_solve(cp, th0, st0, go0, sdf0, 100, 1e-4)
+    a1.record(stream)
+    barrier()
+    n_it = float(sol[1].sum().item())
+    extras['gn_solve_max_iters_100'] = {'ms': a0.elapsed_time(a1), 'mean_iters': n_it / B,
+                                        'problem_iters_per_sec': n_it / (a0.elapsed_time(a1) * 1e-3)}
+    cp.B = B
     clocks = sampler.stop() if sampler is not None else None
 
     if rank != 0:
@@ -389,6 +432,7 @@ def main():
                    'io_dtype': 'f32', 'iterate': ITERATE, 'parallelism': 'batch-sharded x%d, no data-path collective' % world,
                    'l2': 'rotating %d input sets (%.0f MiB) > 126 MB L2' % (N_SETS, N_SETS * (B * IM_SIZE * IM_SIZE * 4 + B * T * d * 4) / 2 ** 20),
                    'state_iters_per_sec': value * T, 'batch_iters_per_sec': value / (world * B), 'launch': shape,
+                   'extras': extras,
                    'e2e_sdf_resident': {'value': e2e_res, 'unit': UNIT, 'h2d_bytes_per_step': hs.h2d_bytes,
                                         'note': 'SDF copied once and kept on the device (GN iterations on fixed environments)'}},
         'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': hs.h2d_bytes + hs.sdf_bytes,
