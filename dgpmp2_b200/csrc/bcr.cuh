@@ -37,10 +37,19 @@
 #define DGPMP2_BCR_STAMP(i) do { } while (0)
 #endif
 
+// profiling aid (scratch/rep_prof.py): -DDGPMP2_REPEAT=n -DDGPMP2_REPEAT_WHAT=1|2|3 -DDGPMP2_REPEAT_LEVEL=l repeats
+// one phase of one level n times (results become meaningless) so that ncu's per-kernel counters describe that phase
+#if defined(DGPMP2_REPEAT)
+#define DGPMP2_REP(what, l) for (int rep_ = 0; rep_ < (((what) == DGPMP2_REPEAT_WHAT && (l) == DGPMP2_REPEAT_LEVEL) ? DGPMP2_REPEAT : 1); ++rep_)
+#else
+#define DGPMP2_REP(what, l)
+#endif
+
 namespace dgpmp2 {
 
 constexpr int kMaxLevels = 16;
 constexpr int kLPN = 4;
+constexpr int kWideMinDefault = 64;   // work items in the CTA from which a level runs one lane per item
 
 __host__ __device__ __forceinline__ int bcr_n_elim(int T, int s) { return (T + s - 1) / (2 * s); }   // nodes j = s(2q+1) < T
 __host__ __device__ __forceinline__ int bcr_n_kept(int T, int s) { return (T + 2 * s - 1) / (2 * s); } // nodes i = 2sq < T
@@ -94,12 +103,25 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
 #pragma unroll
   for (int it = 0; it < 2; ++it) {   // seed is good to ~2^-22: two Newton steps reach double precision
-    const double t = x * y;
-    const double h = 0.5 * y;
+    const double t = __dmul_rn(x, y);
+    const double h = __dmul_rn(0.5, y);
     const double r = fma(-t, h, 0.5);
     y = fma(y, r, y);
   }
   return y;
+}
+
+// c - a * b with a single rounding.  Every multiply-add of the factorisation is written with explicit
+// fma / __dmul_rn / __dadd_rn so that the compiler's contraction choices cannot differ between the
+// LPN = 1 and LPN = 4 instantiations: a problem's result is bit-identical wherever it sits in a CTA.
+__device__ __forceinline__ double fnma(double a, double b, double c) { return fma(-a, b, c); }
+// a . b over D entries, accumulated left to right
+template <int D>
+__device__ __forceinline__ double dot(const double (&a)[D], const double (&b)[D]) {
+  double s = __dmul_rn(a[0], b[0]);
+#pragma unroll
+  for (int k = 1; k < D; ++k) s = fma(a[k], b[k], s);
+  return s;
 }
 
 // In-register Cholesky of a packed lower triangle; the diagonal is replaced by 1/l_kk.
@@ -114,11 +136,11 @@ __device__ __forceinline__ bool chol_packed(double (&L)[D * (D + 1) / 2]) {
     const double rk = fast_rsqrt(akk);
     L[tri(k, k)] = rk;
 #pragma unroll
-    for (int i = k + 1; i < D; ++i) L[tri(i, k)] *= rk;
+    for (int i = k + 1; i < D; ++i) L[tri(i, k)] = __dmul_rn(L[tri(i, k)], rk);
 #pragma unroll
     for (int j = k + 1; j < D; ++j)
 #pragma unroll
-      for (int i = j; i < D; ++i) L[tri(i, j)] -= L[tri(i, k)] * L[tri(j, k)];
+      for (int i = j; i < D; ++i) L[tri(i, j)] = fnma(L[tri(i, k)], L[tri(j, k)], L[tri(i, j)]);
   }
   return ok;
 }
@@ -129,8 +151,8 @@ __device__ __forceinline__ void fwd_solve(const double (&L)[D * (D + 1) / 2], do
   for (int a = 0; a < D; ++a) {
     double s = v[a];
 #pragma unroll
-    for (int c = 0; c < a; ++c) s -= L[tri(a, c)] * v[c];
-    v[a] = s * L[tri(a, a)];
+    for (int c = 0; c < a; ++c) s = fnma(L[tri(a, c)], v[c], s);
+    v[a] = __dmul_rn(s, L[tri(a, a)]);
   }
 }
 
@@ -140,8 +162,8 @@ __device__ __forceinline__ void bwd_solve(const double (&L)[D * (D + 1) / 2], do
   for (int a = D - 1; a >= 0; --a) {
     double s = v[a];
 #pragma unroll
-    for (int c = a + 1; c < D; ++c) s -= L[tri(c, a)] * v[c];
-    v[a] = s * L[tri(a, a)];
+    for (int c = a + 1; c < D; ++c) s = fnma(L[tri(c, a)], v[c], s);
+    v[a] = __dmul_rn(s, L[tri(a, a)]);
   }
 }
 
@@ -194,45 +216,53 @@ __device__ __forceinline__ LevelDiv make_level_div(int n) {
   return d;
 }
 
-// Factor + solve the CTA's np problems.  `nodes` = first record of problem 0 (np * T records,
-// problem-major).  The work items of a level are enumerated across ALL problems of the CTA
-// (item m -> problem m / n_items, node m % n_items) and packed onto consecutive lane groups, so
-// the sparse deep levels of several problems share warps.  Thread tid is lane (tid % LPN) of items
-// tid / LPN, tid / LPN + blockDim / LPN, ...
-// On exit every record's [oR, oR+D) holds x_t.  fail[p] (shared, pre-zeroed) receives t+1 of a node
-// of problem p whose pivot was not positive.  Must be called by ALL threads of the CTA (barriers).
-template <int D>
-__device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int* __restrict__ lvl_off, int nlev,
-                                          int T, int np, int* fail) {
+// ---------------------------------------------------------------------------------------------
+// The three per-level phases, templated on LPN = lanes per work item.
+//   LPN = 4: the lanes of an item split its columns / rows -> shortest dependent chain; used for the
+//            narrow (deep) levels, which are latency bound.
+//   LPN = 1: one lane per item, every access is a 128-bit LDS/STS at the same field offset of
+//            consecutive records (bank-conflict free by the record stride) and nothing is loaded
+//            twice -> about half the shared-memory wavefronts per item; used for the wide levels,
+//            which are bound by the shared-memory pipe (profiles/README.md, isolated-phase runs).
+// All functions must be called by every thread of the CTA with uniform arguments.
+// ---------------------------------------------------------------------------------------------
+
+// (a) factor the eliminated nodes j = s(2e+1): L_j, E_j = L^-1 U_{j-s}^T, F_j = L^-1 U_j, g_j = L^-1 r_j
+template <int D, int LPN>
+__device__ __forceinline__ void bcr_elim_level(double* __restrict__ nodes, const int* __restrict__ lvl_off, int T, int np,
+                                               int s, int ne, int off_l, int* fail) {
   using N = Node<D>;
-  constexpr int DS = N::DS, S = N::kStride, LPN = kLPN;
-  constexpr int NCL = (D + LPN - 1) / LPN;                             // columns / rows per lane
+  constexpr int DS = N::DS, S = N::kStride;
+  constexpr int NCL = (D + LPN - 1) / LPN;                             // columns per lane
   const int e0 = threadIdx.x / LPN, lane = threadIdx.x % LPN;
   const int EPP = blockDim.x / LPN;
-
-  // ------------------------------ forward elimination ------------------------------
-  int off_l = 0;
-  for (int l = 1; l <= nlev; ++l) {
-    const int s = 1 << (l - 1);
-    const int ne = (T + s - 1) >> l;          // bcr_n_elim(T, s), 2s = 2^l
-    // (a) factor the eliminated nodes; the lanes of an item split the columns of [U_i^T | U_j]
-    const LevelDiv dv_e = make_level_div(ne);
-    for (int base = 0; base < np * ne; base += EPP) {   // uniform trip count for the whole CTA
-      const int m = base + e0;
-      const bool on = m < np * ne;
-      const unsigned m_el = __ballot_sync(0xffffffffu, on);
-      if (on) {
-        int p, e;
-        dv_e.split(m, p, e);
-        double* pn = nodes + (size_t)p * T * S;
-        const int j = s * (2 * e + 1);
-        double* nj = pn + (size_t)(off_l + e) * S;
-        const double* ni = pn + (size_t)bcr_slot(lvl_off, T, j - s) * S;
-        const bool has_right = (j + s) < T;
-        double L[DS];
-        ld_lower<D>(nj + N::oD, L);
-        // this lane's columns: issue their loads before the Cholesky chain
-        double ve[NCL][D], vf[NCL][D], vg[D];
+  const LevelDiv dv_e = make_level_div(ne);
+  for (int base = 0; base < np * ne; base += EPP) {   // uniform trip count for the whole CTA
+    const int m = base + e0;
+    const bool on = m < np * ne;
+    const unsigned m_el = (LPN > 1) ? __ballot_sync(0xffffffffu, on) : 0u;
+    if (on) {
+      int p, e;
+      dv_e.split(m, p, e);
+      double* pn = nodes + (size_t)p * T * S;
+      const int j = s * (2 * e + 1);
+      double* nj = pn + (size_t)(off_l + e) * S;
+      const double* ni = pn + (size_t)bcr_slot(lvl_off, T, j - s) * S;
+      const bool has_right = (j + s) < T;
+      double L[DS];
+      ld_lower<D>(nj + N::oD, L);
+      // this lane's columns: issue their loads before the Cholesky chain
+      double ve[NCL][D], vf[NCL][D], vg[D];
+      if constexpr (LPN == 1) {
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          double row[D];
+          ld_vec<D>(nj + N::oU + a * D, row);                         // row a of U_j -> transposed in registers
+#pragma unroll
+          for (int c = 0; c < D; ++c) vf[c][a] = has_right ? row[c] : 0.0;
+          ld_vec<D>(ni + N::oU + a * D, ve[a]);                       // row a of U_i = column a of U_i^T
+        }
+      } else {
 #pragma unroll
         for (int q = 0; q < NCL; ++q) {
           const int c = lane + q * LPN;
@@ -242,41 +272,99 @@ __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int*
             for (int a = 0; a < D; ++a) vf[q][a] = has_right ? nj[N::oU + a * D + c] : 0.0;   // column c of U_j (row-major)
           }
         }
-        ld_vec<D>(nj + N::oR, vg);
-        __syncwarp(m_el);   // every lane of the item has read D_j, U_j, r_j before they are overwritten
-        if (!chol_packed<D>(L)) atomicMax(&fail[p], j + 1);
-        if (lane == 0) {
-#pragma unroll
-          for (int k = 0; k < DS; k += 2) sts2(nj + N::oD + k, L[k], (k + 1 < DS) ? L[k + 1] : 0.0);
-        }
-#pragma unroll
-        for (int q = 0; q < NCL; ++q) {
-          const int c = lane + q * LPN;
-          if (c < D) {
-            fwd_solve<D>(L, ve[q]);
-            fwd_solve<D>(L, vf[q]);
-            st_vec<D>(nj + N::oE + c * D, ve[q]);                     // column c of E_j, column-major
-            st_vec<D>(nj + N::oU + c * D, vf[q]);                     // column c of F_j, column-major, in place
-          }
-        }
-        fwd_solve<D>(L, vg);
-        if (lane == 0) st_vec<D>(nj + N::oR, vg);
       }
+      ld_vec<D>(nj + N::oR, vg);
+      if constexpr (LPN > 1) __syncwarp(m_el);   // every lane of the item has read D_j, U_j, r_j before they are overwritten
+      if (!chol_packed<D>(L)) atomicMax(&fail[p], j + 1);
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < DS; k += 2) sts2(nj + N::oD + k, L[k], (k + 1 < DS) ? L[k + 1] : 0.0);
+      }
+#pragma unroll
+      for (int q = 0; q < NCL; ++q) {
+        const int c = lane + q * LPN;
+        if (c < D) {
+          fwd_solve<D>(L, ve[q]);
+          fwd_solve<D>(L, vf[q]);
+          st_vec<D>(nj + N::oE + c * D, ve[q]);                     // column c of E_j, column-major
+          st_vec<D>(nj + N::oU + c * D, vf[q]);                     // column c of F_j, column-major, in place
+        }
+      }
+      fwd_solve<D>(L, vg);
+      if (lane == 0) st_vec<D>(nj + N::oR, vg);
     }
-    __syncthreads();
-    DGPMP2_BCR_STAMP(8 + 2 * l);
-    // (b) Schur-complement update of the kept nodes; the lanes of an item split the rows of (D_i, r_i, U_i')
-    const int nk = (T + 2 * s - 1) >> l;      // bcr_n_kept(T, s)
-    const LevelDiv dv_k = make_level_div(nk);
-    for (int m = e0; m < np * nk; m += EPP) {
-      int p, e;
-      dv_k.split(m, p, e);
-      double* pn = nodes + (size_t)p * T * S;
-      const int i = 2 * s * e;
-      double* ni = pn + (size_t)bcr_slot(lvl_off, T, i) * S;
-      const bool has_l = e > 0, has_r = (i + s) < T, has_rr = (i + 2 * s) < T;
-      const double* nl = pn + (size_t)(off_l + (has_l ? e - 1 : 0)) * S;   // j = i - s
-      const double* nr = pn + (size_t)(off_l + (has_r ? e : 0)) * S;       // j = i + s
+  }
+}
+
+// (b) Schur-complement update of the kept nodes i = 2se:
+//   D_i -= F_l^T F_l + E_r^T E_r,  r_i -= F_l^T g_l + E_r^T g_r,  U_i' = -E_r^T F_r   (l: j = i - s, r: j = i + s)
+template <int D, int LPN>
+__device__ __forceinline__ void bcr_kept_level(double* __restrict__ nodes, const int* __restrict__ lvl_off, int T, int np,
+                                               int s, int nk, int off_l) {
+  using N = Node<D>;
+  constexpr int S = N::kStride;
+  constexpr int NCL = (D + LPN - 1) / LPN;                             // rows per lane
+  const int e0 = threadIdx.x / LPN, lane = threadIdx.x % LPN;
+  const int EPP = blockDim.x / LPN;
+  const LevelDiv dv_k = make_level_div(nk);
+  for (int m = e0; m < np * nk; m += EPP) {
+    int p, e;
+    dv_k.split(m, p, e);
+    double* pn = nodes + (size_t)p * T * S;
+    const int i = 2 * s * e;
+    double* ni = pn + (size_t)bcr_slot(lvl_off, T, i) * S;
+    const bool has_l = e > 0, has_r = (i + s) < T, has_rr = (i + 2 * s) < T;
+    const double* nl = pn + (size_t)(off_l + (has_l ? e - 1 : 0)) * S;   // j = i - s
+    const double* nr = pn + (size_t)(off_l + (has_r ? e : 0)) * S;       // j = i + s
+    if constexpr (LPN == 1) {
+      // only the lower triangle of D_i is ever read (ld_lower); the strict upper part is written as its mirror
+      double Dl[N::DS], r[D];
+      ld_lower<D>(ni + N::oD, Dl);
+      ld_vec<D>(ni + N::oR, r);
+      if (has_l) {
+        double F[D][D], g[D];                                          // F[c][k] = F_l(k, c)
+#pragma unroll
+        for (int c = 0; c < D; ++c) ld_vec<D>(nl + N::oU + c * D, F[c]);
+        ld_vec<D>(nl + N::oR, g);
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          r[a] = __dsub_rn(r[a], dot<D>(F[a], g));
+#pragma unroll
+          for (int c = 0; c <= a; ++c) Dl[tri(a, c)] = __dsub_rn(Dl[tri(a, c)], dot<D>(F[a], F[c]));
+        }
+      }
+      double Em[D][D];                                                 // Em[c][k] = E_r(k, c)
+      if (has_r) {
+        double g[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) ld_vec<D>(nr + N::oE + c * D, Em[c]);
+        ld_vec<D>(nr + N::oR, g);
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          r[a] = __dsub_rn(r[a], dot<D>(Em[a], g));
+#pragma unroll
+          for (int c = 0; c <= a; ++c) Dl[tri(a, c)] = __dsub_rn(Dl[tri(a, c)], dot<D>(Em[a], Em[c]));
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int c = 0; c < D; c += 2)
+          sts2(ni + N::oD + a * D + c, (c <= a) ? Dl[tri(a, c)] : Dl[tri(c, a)], (c + 1 <= a) ? Dl[tri(a, c + 1)] : Dl[tri(c + 1, a)]);
+      st_vec<D>(ni + N::oR, r);
+      if (has_rr) {   // has_rr implies has_r
+        double un[D][D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double fc[D];
+          ld_vec<D>(nr + N::oU + c * D, fc);
+#pragma unroll
+          for (int a = 0; a < D; ++a) un[a][c] = -dot<D>(Em[a], fc);
+        }
+#pragma unroll
+        for (int a = 0; a < D; ++a) st_vec<D>(ni + N::oU + a * D, un[a]);   // new coupling to i + 2s, row-major
+      }
+    } else {
 #pragma unroll
       for (int q = 0; q < NCL; ++q) {
         const int a = lane + q * LPN;
@@ -290,34 +378,26 @@ __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int*
             double fa[D], g[D];
             ld_vec<D>(nl + N::oU + a * D, fa);
             ld_vec<D>(nl + N::oR, g);
-#pragma unroll
-            for (int k = 0; k < D; ++k) ra -= fa[k] * g[k];
+            ra = __dsub_rn(ra, dot<D>(fa, g));
 #pragma unroll
             for (int c = 0; c < D; ++c) {
               double fc[D];
               ld_vec<D>(nl + N::oU + c * D, fc);
-              double s0 = 0.0;
-#pragma unroll
-              for (int k = 0; k < D; ++k) s0 += fa[k] * fc[k];
-              drow[c] -= s0;
+              drow[c] = __dsub_rn(drow[c], dot<D>(fa, fc));
             }
           }
           if (has_r) {   // D_i -= E^T E, r_i -= E^T g, U_i' = -E^T F with E, F, g of j = i + s
             double ea[D], g[D];
             ld_vec<D>(nr + N::oE + a * D, ea);
             ld_vec<D>(nr + N::oR, g);
-#pragma unroll
-            for (int k = 0; k < D; ++k) ra -= ea[k] * g[k];
+            ra = __dsub_rn(ra, dot<D>(ea, g));
 #pragma unroll
             for (int c = 0; c < D; ++c) {
               double ec[D], fc[D];
               ld_vec<D>(nr + N::oE + c * D, ec);
               ld_vec<D>(nr + N::oU + c * D, fc);
-              double s0 = 0.0, t0 = 0.0;
-#pragma unroll
-              for (int k = 0; k < D; ++k) { s0 += ea[k] * ec[k]; t0 += ea[k] * fc[k]; }
-              drow[c] -= s0;
-              unew[c] = -t0;
+              drow[c] = __dsub_rn(drow[c], dot<D>(ea, ec));
+              unew[c] = -dot<D>(ea, fc);
             }
           }
           st_vec<D>(ni + N::oD + a * D, drow);
@@ -326,6 +406,121 @@ __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int*
         }
       }
     }
+  }
+}
+
+// (c) back substitution of the nodes eliminated at this level: x_j = L_j^-T (g_j - E_j x_{j-s} - F_j x_{j+s})
+template <int D, int LPN>
+__device__ __forceinline__ void bcr_back_level(double* __restrict__ nodes, const int* __restrict__ lvl_off, int T, int np,
+                                               int s, int ne, int off_l) {
+  using N = Node<D>;
+  constexpr int DS = N::DS, S = N::kStride;
+  constexpr int NCL = (D + LPN - 1) / LPN;                             // rows per lane
+  const int e0 = threadIdx.x / LPN, lane = threadIdx.x % LPN;
+  const int EPP = blockDim.x / LPN;
+  const LevelDiv dv_e = make_level_div(ne);
+  for (int base = 0; base < np * ne; base += EPP) {
+    const int m = base + e0;
+    const bool on = m < np * ne;
+    const unsigned m_bs = (LPN > 1) ? __ballot_sync(0xffffffffu, on) : 0u;
+    if (on) {
+      int p, e;
+      dv_e.split(m, p, e);
+      double* pn = nodes + (size_t)p * T * S;
+      const int j = s * (2 * e + 1);
+      double* nj = pn + (size_t)(off_l + e) * S;
+      const double* ni = pn + (size_t)bcr_slot(lvl_off, T, j - s) * S;
+      const bool has_right = (j + s) < T;
+      const double* nk2 = has_right ? pn + (size_t)bcr_slot(lvl_off, T, j + s) * S : ni;
+      double xl[D], xr[D], L[DS];
+      ld_vec<D>(ni + N::oR, xl);
+      ld_vec<D>(nk2 + N::oR, xr);
+#pragma unroll
+      for (int c = 0; c < D; ++c) xr[c] = has_right ? xr[c] : 0.0;
+#pragma unroll
+      for (int k = 0; k < DS; k += 2) {
+        const double2 t = lds2(nj + N::oD + k);
+        L[k] = t.x;
+        if (k + 1 < DS) L[k + 1] = t.y;
+      }
+      if constexpr (LPN == 1) {
+        double v[D], w[D];
+        ld_vec<D>(nj + N::oR, v);
+#pragma unroll
+        for (int a = 0; a < D; ++a) w[a] = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double ec[D], fc[D];
+          ld_vec<D>(nj + N::oE + c * D, ec);
+          ld_vec<D>(nj + N::oU + c * D, fc);
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            v[a] = fnma(ec[a], xl[c], v[a]);
+            w[a] = fnma(fc[a], xr[c], w[a]);
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < D; ++a) v[a] = __dadd_rn(v[a], w[a]);
+        bwd_solve<D>(L, v);
+        st_vec<D>(nj + N::oR, v);
+      } else {
+        // each lane forms its rows of v = g_j - E_j x_{j-s} - F_j x_{j+s} and publishes them in place of g_j
+#pragma unroll
+        for (int q = 0; q < NCL; ++q) {
+          const int a = lane + q * LPN;
+          if (a < D) {
+            double va = nj[N::oR + a], vb = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              va = fnma(nj[N::oE + c * D + a], xl[c], va);
+              vb = fnma(nj[N::oU + c * D + a], xr[c], vb);
+            }
+            nj[N::oR + a] = __dadd_rn(va, vb);
+          }
+        }
+        __syncwarp(m_bs);
+        double v[D];
+        ld_vec<D>(nj + N::oR, v);
+        bwd_solve<D>(L, v);
+        __syncwarp(m_bs);   // all lanes have read v before any lane overwrites it with x_j
+#pragma unroll
+        for (int q = 0; q < NCL; ++q) {
+          const int a = lane + q * LPN;
+          if (a < D) nj[N::oR + a] = v[a];
+        }
+      }
+    }
+  }
+}
+
+// Factor + solve the CTA's np problems.  `nodes` = first record of problem 0 (np * T records,
+// problem-major).  The work items of a level are enumerated across ALL problems of the CTA
+// (item m -> problem m / n_items, node m % n_items) and packed onto consecutive lane groups, so
+// the sparse deep levels of several problems share warps.  A level whose items, at kLPN lanes each,
+// would need more than `wide_passes` sweeps of the CTA runs with one lane per item instead.
+// On exit every record's [oR, oR+D) holds x_t.  fail[p] (shared, pre-zeroed) receives t+1 of a node
+// of problem p whose pivot was not positive.  Must be called by ALL threads of the CTA (barriers).
+template <int D>
+__device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int* __restrict__ lvl_off, int nlev,
+                                          int T, int np, int wide_min, int* fail) {
+  using N = Node<D>;
+  constexpr int DS = N::DS, S = N::kStride;
+
+  // ------------------------------ forward elimination ------------------------------
+  int off_l = 0;
+  for (int l = 1; l <= nlev; ++l) {
+    const int s = 1 << (l - 1);
+    const int ne = (T + s - 1) >> l;          // bcr_n_elim(T, s), 2s = 2^l
+    const int nk = (T + 2 * s - 1) >> l;      // bcr_n_kept(T, s)
+    const bool wide = np * ne >= wide_min;    // uniform
+    DGPMP2_REP(1, l)
+    if (wide) bcr_elim_level<D, 1>(nodes, lvl_off, T, np, s, ne, off_l, fail);
+    else      bcr_elim_level<D, kLPN>(nodes, lvl_off, T, np, s, ne, off_l, fail);
+    __syncthreads();
+    DGPMP2_BCR_STAMP(8 + 2 * l);
+    DGPMP2_REP(2, l)
+    if (wide) bcr_kept_level<D, 1>(nodes, lvl_off, T, np, s, nk, off_l);
+    else      bcr_kept_level<D, kLPN>(nodes, lvl_off, T, np, s, nk, off_l);
     __syncthreads();
     DGPMP2_BCR_STAMP(9 + 2 * l);
     off_l += ne;
@@ -350,57 +545,9 @@ __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int*
     const int s = 1 << (l - 1);
     const int ne = (T + s - 1) >> l;
     off_l -= ne;
-    const LevelDiv dv_e = make_level_div(ne);
-    for (int base = 0; base < np * ne; base += EPP) {
-      const int m = base + e0;
-      const bool on = m < np * ne;
-      const unsigned m_bs = __ballot_sync(0xffffffffu, on);
-      if (on) {
-        int p, e;
-        dv_e.split(m, p, e);
-        double* pn = nodes + (size_t)p * T * S;
-        const int j = s * (2 * e + 1);
-        double* nj = pn + (size_t)(off_l + e) * S;
-        const double* ni = pn + (size_t)bcr_slot(lvl_off, T, j - s) * S;
-        const bool has_right = (j + s) < T;
-        const double* nk2 = has_right ? pn + (size_t)bcr_slot(lvl_off, T, j + s) * S : ni;
-        double xl[D], xr[D], L[DS];
-        ld_vec<D>(ni + N::oR, xl);
-        ld_vec<D>(nk2 + N::oR, xr);
-#pragma unroll
-        for (int c = 0; c < D; ++c) xr[c] = has_right ? xr[c] : 0.0;
-#pragma unroll
-        for (int k = 0; k < DS; k += 2) {
-          const double2 t = lds2(nj + N::oD + k);
-          L[k] = t.x;
-          if (k + 1 < DS) L[k + 1] = t.y;
-        }
-        // each lane forms its rows of v = g_j - E_j x_{j-s} - F_j x_{j+s} and publishes them in place of g_j
-#pragma unroll
-        for (int q = 0; q < NCL; ++q) {
-          const int a = lane + q * LPN;
-          if (a < D) {
-            double va = nj[N::oR + a], vb = 0.0;
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-              va -= nj[N::oE + c * D + a] * xl[c];
-              vb -= nj[N::oU + c * D + a] * xr[c];
-            }
-            nj[N::oR + a] = va + vb;
-          }
-        }
-        __syncwarp(m_bs);
-        double v[D];
-        ld_vec<D>(nj + N::oR, v);
-        bwd_solve<D>(L, v);
-        __syncwarp(m_bs);   // all lanes have read v before any lane overwrites it with x_j
-#pragma unroll
-        for (int q = 0; q < NCL; ++q) {
-          const int a = lane + q * LPN;
-          if (a < D) nj[N::oR + a] = v[a];
-        }
-      }
-    }
+    DGPMP2_REP(3, l)
+    if (np * ne >= wide_min) bcr_back_level<D, 1>(nodes, lvl_off, T, np, s, ne, off_l);
+    else                     bcr_back_level<D, kLPN>(nodes, lvl_off, T, np, s, ne, off_l);
     __syncthreads();
     DGPMP2_BCR_STAMP(40 + l);
   }

@@ -39,6 +39,13 @@ int check_params(const dgpmp2_params* p, const dgpmp2_weights* w) {
   return DGPMP2_OK;
 }
 
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  if (e == nullptr) return dflt;
+  const int v = atoi(e);
+  return v > 0 ? v : dflt;
+}
+
 KParams make_kparams(const dgpmp2_params* p) {
   KParams k;
   memset(&k, 0, sizeof(k));
@@ -91,6 +98,7 @@ KParams make_kparams(const dgpmp2_params* p) {
   bcr_make_levels(p->T, lv);
   k.nlev = lv.nlev;
   for (int l = 0; l < 18; ++l) k.lvl_off[l] = (l <= lv.nlev + 1) ? lv.off[l] : 0;
+  k.wide_min = env_int("DGPMP2_WIDE", kWideMinDefault);
   return k;
 }
 
@@ -117,13 +125,6 @@ KWeights<IO> make_kweights(const dgpmp2_weights* w) {
 }
 
 struct LaunchShape { int np, tpp, threads, smem, grid; };
-
-int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  if (e == nullptr) return dflt;
-  const int v = atoi(e);
-  return v > 0 ? v : dflt;
-}
 
 int sm_count() {
   static int cached[64] = {0};

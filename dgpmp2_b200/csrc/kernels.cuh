@@ -151,7 +151,7 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
   __syncthreads();
   DGPMP2_STAMP(2);
 
-  bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, S.fail);   // ends with a barrier
+  bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, P.wide_min, S.fail);   // ends with a barrier
   DGPMP2_STAMP(3);
 
   {  // dth, natural order -> coalesced stores
@@ -220,7 +220,7 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
     for (int p = 0; p < np; ++p) all_done = all_done && (done[p] == 2);
     if (all_done || last) break;
 
-    bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, S.fail);
+    bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, P.wide_min, S.fail);
 
     // th <- th + dth for problems still running; |dth|^2 partials
     for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
@@ -308,7 +308,7 @@ gn_step_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict_
   }
   __syncthreads();
 
-  bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, S.fail);   // lambda in every record's [oR, oR+D)
+  bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, P.wide_min, S.fail);   // lambda in every record's [oR, oR+D)
 
   const double invM = 1.0 / (double)P.M;
   const float inv_T = 1.0f / (float)T;
