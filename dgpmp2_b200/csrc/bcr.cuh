@@ -50,6 +50,7 @@ namespace dgpmp2 {
 constexpr int kMaxLevels = 16;
 constexpr int kLPN = 4;
 constexpr int kWideMinDefault = 64;   // work items in the CTA from which a level runs one lane per item
+constexpr int kTailMaxDefault = 4;    // elimination stops at this many nodes per problem; the rest is solved sequentially
 
 __host__ __device__ __forceinline__ int bcr_n_elim(int T, int s) { return (T + s - 1) / (2 * s); }   // nodes j = s(2q+1) < T
 __host__ __device__ __forceinline__ int bcr_n_kept(int T, int s) { return (T + 2 * s - 1) / (2 * s); } // nodes i = 2sq < T
@@ -96,19 +97,19 @@ struct Node {
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void sts2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 
-// 1/sqrt(x) for positive normal x: hardware seed + Newton steps, no special-case branches
-// (a non-positive pivot is reported through the status flag, its value is then irrelevant).
+// 1/sqrt(x) for positive normal x: hardware seed + one cubically convergent correction, no special-case
+// branches (a non-positive pivot is reported through the status flag, its value is then irrelevant).
+// With e = 1 - x y0^2:  1/sqrt(x) = y0 (1 - e)^(-1/2) = y0 (1 + e/2 + 3e^2/8 + O(e^3)); the seed is good to
+// ~2^-20, so the O(e^3) remainder is below 2^-60.  Four dependent operations after the MUFU instead of the
+// six of two Newton steps - this sits on the critical path of every Cholesky pivot.
 __device__ __forceinline__ double fast_rsqrt(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {   // seed is good to ~2^-22: two Newton steps reach double precision
-    const double t = __dmul_rn(x, y);
-    const double h = __dmul_rn(0.5, y);
-    const double r = fma(-t, h, 0.5);
-    y = fma(y, r, y);
-  }
-  return y;
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double t = __dmul_rn(x, y0);
+  const double e = fma(-t, y0, 1.0);
+  const double a = __dmul_rn(y0, e);
+  const double p = fma(e, 0.375, 0.5);
+  return fma(a, p, y0);
 }
 
 // c - a * b with a single rounding.  Every multiply-add of the factorisation is written with explicit
@@ -251,18 +252,35 @@ __device__ __forceinline__ void bcr_elim_level(double* __restrict__ nodes, const
       const bool has_right = (j + s) < T;
       double L[DS];
       ld_lower<D>(nj + N::oD, L);
-      // this lane's columns: issue their loads before the Cholesky chain
-      double ve[NCL][D], vf[NCL][D], vg[D];
       if constexpr (LPN == 1) {
+        // two batches ([U_j | r_j], then U_i^T) keep the live set at L + D*D + D doubles: no spills
+        double vf[D][D], vg[D];
 #pragma unroll
         for (int a = 0; a < D; ++a) {
           double row[D];
           ld_vec<D>(nj + N::oU + a * D, row);                         // row a of U_j -> transposed in registers
 #pragma unroll
           for (int c = 0; c < D; ++c) vf[c][a] = has_right ? row[c] : 0.0;
-          ld_vec<D>(ni + N::oU + a * D, ve[a]);                       // row a of U_i = column a of U_i^T
         }
+        ld_vec<D>(nj + N::oR, vg);
+        if (!chol_packed<D>(L)) atomicMax(&fail[p], j + 1);
+#pragma unroll
+        for (int k = 0; k < DS; k += 2) sts2(nj + N::oD + k, L[k], (k + 1 < DS) ? L[k + 1] : 0.0);
+#pragma unroll
+        for (int c = 0; c < D; ++c) fwd_solve<D>(L, vf[c]);
+        fwd_solve<D>(L, vg);
+#pragma unroll
+        for (int c = 0; c < D; ++c) st_vec<D>(nj + N::oU + c * D, vf[c]);   // F_j column-major, in place
+        st_vec<D>(nj + N::oR, vg);
+#pragma unroll
+        for (int c = 0; c < D; ++c) ld_vec<D>(ni + N::oU + c * D, vf[c]);   // row c of U_i = column c of U_i^T
+#pragma unroll
+        for (int c = 0; c < D; ++c) fwd_solve<D>(L, vf[c]);
+#pragma unroll
+        for (int c = 0; c < D; ++c) st_vec<D>(nj + N::oE + c * D, vf[c]);   // E_j column-major
       } else {
+        // this lane's columns: issue their loads before the Cholesky chain
+        double ve[NCL][D], vf[NCL][D], vg[D];
 #pragma unroll
         for (int q = 0; q < NCL; ++q) {
           const int c = lane + q * LPN;
@@ -272,26 +290,26 @@ __device__ __forceinline__ void bcr_elim_level(double* __restrict__ nodes, const
             for (int a = 0; a < D; ++a) vf[q][a] = has_right ? nj[N::oU + a * D + c] : 0.0;   // column c of U_j (row-major)
           }
         }
-      }
-      ld_vec<D>(nj + N::oR, vg);
-      if constexpr (LPN > 1) __syncwarp(m_el);   // every lane of the item has read D_j, U_j, r_j before they are overwritten
-      if (!chol_packed<D>(L)) atomicMax(&fail[p], j + 1);
-      if (lane == 0) {
+        ld_vec<D>(nj + N::oR, vg);
+        __syncwarp(m_el);   // every lane of the item has read D_j, U_j, r_j before they are overwritten
+        if (!chol_packed<D>(L)) atomicMax(&fail[p], j + 1);
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < DS; k += 2) sts2(nj + N::oD + k, L[k], (k + 1 < DS) ? L[k + 1] : 0.0);
-      }
-#pragma unroll
-      for (int q = 0; q < NCL; ++q) {
-        const int c = lane + q * LPN;
-        if (c < D) {
-          fwd_solve<D>(L, ve[q]);
-          fwd_solve<D>(L, vf[q]);
-          st_vec<D>(nj + N::oE + c * D, ve[q]);                     // column c of E_j, column-major
-          st_vec<D>(nj + N::oU + c * D, vf[q]);                     // column c of F_j, column-major, in place
+          for (int k = 0; k < DS; k += 2) sts2(nj + N::oD + k, L[k], (k + 1 < DS) ? L[k + 1] : 0.0);
         }
+#pragma unroll
+        for (int q = 0; q < NCL; ++q) {
+          const int c = lane + q * LPN;
+          if (c < D) {
+            fwd_solve<D>(L, ve[q]);
+            fwd_solve<D>(L, vf[q]);
+            st_vec<D>(nj + N::oE + c * D, ve[q]);                     // column c of E_j, column-major
+            st_vec<D>(nj + N::oU + c * D, vf[q]);                     // column c of F_j, column-major, in place
+          }
+        }
+        fwd_solve<D>(L, vg);
+        if (lane == 0) st_vec<D>(nj + N::oR, vg);
       }
-      fwd_solve<D>(L, vg);
-      if (lane == 0) st_vec<D>(nj + N::oR, vg);
     }
   }
 }
@@ -493,22 +511,129 @@ __device__ __forceinline__ void bcr_back_level(double* __restrict__ nodes, const
   }
 }
 
+// (d) the chain that is left once the kept nodes are few: nodes t = S e, e = 0..nc-1, coupled through U.
+// Solved by sequential block Cholesky (block Thomas) with kLPN lanes per problem: a step costs one
+// Cholesky chain, one __syncwarp and no CTA barrier, which beats another elimination level (three
+// phases, two CTA barriers) as soon as nc is small.
+//   forward:  D_e' = D_e - F_{e-1}^T F_{e-1},  L_e L_e^T = D_e',  F_e = L_e^-1 U_e,  g_e = L_e^-1 (r_e - F_{e-1}^T g_{e-1})
+//   backward: x_e = L_e^-T (g_e - F_e x_{e+1})
+// Every lane forms D_e', its Cholesky factor, g_e and the whole back substitution redundantly (no
+// exchange needed); the lanes only split the columns of F_e, which travel through the record.
+// With nc == 1 this is the classic root solve of cyclic reduction.
+template <int D>
+__device__ __forceinline__ void bcr_tail(double* __restrict__ nodes, const int* __restrict__ lvl_off, int T, int np,
+                                         int S_t, int nc, int* fail) {
+  using N = Node<D>;
+  constexpr int DS = N::DS, S = N::kStride, LPN = kLPN;
+  constexpr int NCL = (D + LPN - 1) / LPN;
+  const int e0 = threadIdx.x / LPN, lane = threadIdx.x % LPN;
+  const int EPP = blockDim.x / LPN;
+  for (int base = 0; base < np; base += EPP) {          // uniform trip count (one pass unless blockDim < 4 np)
+    const int p = base + e0;
+    const bool on = p < np;
+    const unsigned m_t = __ballot_sync(0xffffffffu, on);
+    if (on) {
+      double* pn = nodes + (size_t)p * T * S;
+      double gp[D];
+      const double* prev = pn;
+#pragma unroll 1
+      for (int e = 0; e < nc; ++e) {
+        double* nd = pn + (size_t)bcr_slot(lvl_off, T, S_t * e) * S;
+        const bool has_next = e + 1 < nc;
+        double L[DS], r[D], vf[NCL][D];
+        ld_lower<D>(nd + N::oD, L);
+        ld_vec<D>(nd + N::oR, r);
+#pragma unroll
+        for (int q = 0; q < NCL; ++q) {
+          const int c = lane + q * LPN;
+          if (c < D) {
+#pragma unroll
+            for (int a = 0; a < D; ++a) vf[q][a] = has_next ? nd[N::oU + a * D + c] : 0.0;   // column c of U_e (row-major)
+          }
+        }
+        if (e > 0) {
+          double F[D][D];                                              // F[c][k] = F_{e-1}(k, c)
+#pragma unroll
+          for (int c = 0; c < D; ++c) ld_vec<D>(prev + N::oU + c * D, F[c]);
+#pragma unroll
+          for (int a = 0; a < D; ++a) {
+            r[a] = __dsub_rn(r[a], dot<D>(F[a], gp));
+#pragma unroll
+            for (int c = 0; c <= a; ++c) L[tri(a, c)] = __dsub_rn(L[tri(a, c)], dot<D>(F[a], F[c]));
+          }
+        }
+        __syncwarp(m_t);   // every lane of the problem has read U_e before it is overwritten by F_e
+        if (!chol_packed<D>(L)) atomicMax(&fail[p], S_t * e + 1);
+        fwd_solve<D>(L, r);
+#pragma unroll
+        for (int q = 0; q < NCL; ++q) {
+          const int c = lane + q * LPN;
+          if (c < D && has_next) {
+            fwd_solve<D>(L, vf[q]);
+            st_vec<D>(nd + N::oU + c * D, vf[q]);                      // column c of F_e, column-major, in place
+          }
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < DS; k += 2) sts2(nd + N::oD + k, L[k], (k + 1 < DS) ? L[k + 1] : 0.0);
+          st_vec<D>(nd + N::oR, r);
+        }
+#pragma unroll
+        for (int a = 0; a < D; ++a) gp[a] = r[a];
+        prev = nd;
+        __syncwarp(m_t);   // F_e, L_e, g_e are visible to the other lanes of the problem
+      }
+      DGPMP2_BCR_STAMP(6);
+      double x[D];
+#pragma unroll
+      for (int a = 0; a < D; ++a) x[a] = 0.0;
+#pragma unroll 1
+      for (int e = nc - 1; e >= 0; --e) {
+        double* nd = pn + (size_t)bcr_slot(lvl_off, T, S_t * e) * S;
+        double L[DS], v[D];
+#pragma unroll
+        for (int k = 0; k < DS; k += 2) {
+          const double2 t = lds2(nd + N::oD + k);
+          L[k] = t.x;
+          if (k + 1 < DS) L[k + 1] = t.y;
+        }
+        ld_vec<D>(nd + N::oR, v);
+        if (e + 1 < nc) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            double fc[D];
+            ld_vec<D>(nd + N::oU + c * D, fc);
+#pragma unroll
+            for (int a = 0; a < D; ++a) v[a] = fnma(fc[a], x[c], v[a]);
+          }
+        }
+        bwd_solve<D>(L, v);
+#pragma unroll
+        for (int a = 0; a < D; ++a) x[a] = v[a];
+        __syncwarp(m_t);   // every lane has read g_e before lane 0 replaces it with x_e
+        if (lane == 0) st_vec<D>(nd + N::oR, v);
+      }
+    }
+  }
+}
+
 // Factor + solve the CTA's np problems.  `nodes` = first record of problem 0 (np * T records,
 // problem-major).  The work items of a level are enumerated across ALL problems of the CTA
 // (item m -> problem m / n_items, node m % n_items) and packed onto consecutive lane groups, so
-// the sparse deep levels of several problems share warps.  A level whose items, at kLPN lanes each,
-// would need more than `wide_passes` sweeps of the CTA runs with one lane per item instead.
+// the sparse deep levels of several problems share warps.  A level with at least `wide_min` items
+// in the CTA runs one lane per item, the others kLPN lanes per item.  Elimination stops as soon as
+// at most `tail_max` nodes per problem are left; that chain is solved sequentially (bcr_tail).
 // On exit every record's [oR, oR+D) holds x_t.  fail[p] (shared, pre-zeroed) receives t+1 of a node
 // of problem p whose pivot was not positive.  Must be called by ALL threads of the CTA (barriers).
 template <int D>
 __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int* __restrict__ lvl_off, int nlev,
-                                          int T, int np, int wide_min, int* fail) {
-  using N = Node<D>;
-  constexpr int DS = N::DS, S = N::kStride;
+                                          int T, int np, int wide_min, int tail_max, int* fail) {
+  int nl = 0;                                 // elimination levels actually run (<= nlev)
+  while (((T + (1 << nl) - 1) >> nl) > tail_max) ++nl;
 
   // ------------------------------ forward elimination ------------------------------
   int off_l = 0;
-  for (int l = 1; l <= nlev; ++l) {
+  for (int l = 1; l <= nl; ++l) {
     const int s = 1 << (l - 1);
     const int ne = (T + s - 1) >> l;          // bcr_n_elim(T, s), 2s = 2^l
     const int nk = (T + 2 * s - 1) >> l;      // bcr_n_kept(T, s)
@@ -526,22 +651,13 @@ __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int*
     off_l += ne;
   }
 
-  // ------------------------------ root (t = 0) ------------------------------
-  for (int p = threadIdx.x; p < np; p += blockDim.x) {
-    double* n0 = nodes + ((size_t)p * T + (T - 1)) * S;
-    double L[DS], v[D];
-    ld_lower<D>(n0 + N::oD, L);
-    ld_vec<D>(n0 + N::oR, v);
-    if (!chol_packed<D>(L)) atomicMax(&fail[p], 1);
-    fwd_solve<D>(L, v);
-    bwd_solve<D>(L, v);
-    st_vec<D>(n0 + N::oR, v);
-  }
+  // ------------------------------ remaining chain (root when tail_max == 1) ------------------------------
+  bcr_tail<D>(nodes, lvl_off, T, np, 1 << nl, (T + (1 << nl) - 1) >> nl, fail);
   __syncthreads();
   DGPMP2_BCR_STAMP(5);
 
   // ------------------------------ back substitution ------------------------------
-  for (int l = nlev; l >= 1; --l) {
+  for (int l = nl; l >= 1; --l) {
     const int s = 1 << (l - 1);
     const int ne = (T + s - 1) >> l;
     off_l -= ne;

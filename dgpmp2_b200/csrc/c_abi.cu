@@ -99,6 +99,7 @@ KParams make_kparams(const dgpmp2_params* p) {
   k.nlev = lv.nlev;
   for (int l = 0; l < 18; ++l) k.lvl_off[l] = (l <= lv.nlev + 1) ? lv.off[l] : 0;
   k.wide_min = env_int("DGPMP2_WIDE", kWideMinDefault);
+  k.tail_max = env_int("DGPMP2_TAIL", kTailMaxDefault);
   return k;
 }
 
@@ -141,7 +142,8 @@ int sm_count() {
 // Problems per CTA (NP) and CTA size.  All problems an SM has to process are put in ONE CTA when
 // they fit (NP = ceil(B / #SMs), bounded by shared memory and the thread limit): the BCR work items
 // of all of them are packed onto consecutive lanes, so the sparse deep levels of several problems
-// share warps, and one CTA per SM launches without a ramp.  Threads = kLPN lanes per level-1 item.
+// share warps, and one CTA per SM launches without a ramp.  Threads = kLPN lanes per level-1 item
+// when that fits the CTA, else one thread per node record.
 template <int D, typename IO>
 int choose_shape(int B, int T, int mode, LaunchShape& s) {
   const int max_threads = (D == 4) ? 512 : 256;
@@ -155,7 +157,12 @@ int choose_shape(int B, int T, int mode, LaunchShape& s) {
   if (bytes > (size_t)kSmemLimit) return DGPMP2_ERR_UNSUPPORTED;
   int threads = kLPN * items * np;
   threads = (threads + 31) / 32 * 32;
-  if (threads > max_threads) threads = max_threads;
+  if (threads > max_threads) {
+    // cannot give every level-1 item its kLPN lanes: one thread per node record (assembly, one-lane levels)
+    // is then enough; more warps would only wait at the barriers
+    threads = (np * T + 31) / 32 * 32;
+    if (threads > max_threads) threads = max_threads;
+  }
   if (threads < 64) threads = 64;
   threads = env_int("DGPMP2_THREADS", threads);
   if (threads > max_threads) threads = max_threads;

@@ -37,6 +37,7 @@ struct KParams {
   // BCR level table (bcr.cuh), computed on the host: lvl_off[l] = first node slot of level l
   int nlev;
   int lvl_off[18];
+  int tail_max;         // elimination stops once at most this many nodes per problem are left (bcr.cuh)
   int wide_min;         // levels with at least this many work items in the CTA run one lane per item (bcr.cuh)
 };
 

@@ -105,6 +105,48 @@ __device__ __forceinline__ void reduce_per_problem(const double* base, int strid
   }
 }
 
+// Same for two interleaved quantities stored as adjacent doubles (16-byte aligned): `base[(p*T + i) * stride + {0, 1}]`.
+// Each component is summed in exactly the order reduce_per_problem uses.  `f(p, sum0, sum1)` is called by lane 0.
+template <typename F>
+__device__ __forceinline__ void reduce2_per_problem(const double* base, int stride, int np, int T, F f) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int p = warp; p < np; p += nwarps) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = lane; i < T; i += 32) {
+      const double2 v = lds2(base + (size_t)(p * T + i) * stride);
+      s0 += v.x;
+      s1 += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane == 0) f(p, s0, s1);
+  }
+}
+
+// one state (D values) to global memory; `vec` (uniform): the array base is 16-byte aligned -> wide stores
+template <int D, typename IO>
+__device__ __forceinline__ void store_state(IO* __restrict__ dst, const double (&x)[D], bool vec) {
+  if (!vec) {
+#pragma unroll
+    for (int a = 0; a < D; ++a) dst[a] = (IO)x[a];
+    return;
+  }
+  if constexpr (sizeof(IO) == 4 && D % 4 == 0) {
+#pragma unroll
+    for (int a = 0; a < D; a += 4)
+      *reinterpret_cast<float4*>(dst + a) = make_float4((float)x[a], (float)x[a + 1], (float)x[a + 2], (float)x[a + 3]);
+  } else if constexpr (sizeof(IO) == 4) {
+#pragma unroll
+    for (int a = 0; a < D; a += 2) *reinterpret_cast<float2*>(dst + a) = make_float2((float)x[a], (float)x[a + 1]);
+  } else {
+#pragma unroll
+    for (int a = 0; a < D; a += 2) *reinterpret_cast<double2*>(dst + a) = make_double2(x[a], x[a + 1]);
+  }
+}
+
 template <int D, typename IO>
 __device__ __forceinline__ void cta_prologue(const KParams& P, const StepSmem<D, IO>& S, int T, int NP, int np,
                                              const IO* __restrict__ th_src, bool solve) {
@@ -151,23 +193,26 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
   __syncthreads();
   DGPMP2_STAMP(2);
 
-  bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, P.wide_min, S.fail);   // ends with a barrier
+  bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, P.wide_min, P.tail_max, S.fail);   // ends with a barrier
   DGPMP2_STAMP(3);
 
   {  // dth, natural order -> coalesced stores
     IO* dst = dth + (size_t)b0 * T * D;
     const int n = np * T;
+    const float inv_T = 1.0f / (float)T;
+    const bool vec = (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0ull;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int p = i / T, t = i - p * T;
+      const int p = fast_div(i, inv_T), t = i - p * T;
       double x[D];
       ld_vec<D>(S.nodes + ((size_t)p * T + bcr_slot(S.lvl_off, T, t)) * N::kStride + N::oR, x);
-#pragma unroll
-      for (int a = 0; a < D; ++a) dst[(size_t)i * D + a] = (IO)x[a];
+      store_state<D, IO>(dst + (size_t)i * D, x, vec);
     }
   }
   const double invM = 1.0 / (double)P.M;
-  reduce_per_problem(S.nodes + N::oX, N::kStride, np, T, [&](int p, double s) { err[b0 + p] = (IO)(s * invM); });
-  reduce_per_problem(S.nodes + N::oX + 1, N::kStride, np, T, [&](int p, double s) { err_ext[b0 + p] = (IO)(s * invM); });
+  reduce2_per_problem(S.nodes + N::oX, N::kStride, np, T, [&](int p, double s0, double s1) {
+    err[b0 + p] = (IO)(s0 * invM);
+    err_ext[b0 + p] = (IO)(s1 * invM);
+  });
   if (status != nullptr)
     for (int p = threadIdx.x; p < np; p += blockDim.x) status[b0 + p] = S.fail[p];
   DGPMP2_STAMP(4);
@@ -203,13 +248,15 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
     assemble_cta<DOF, IO>(P, Wt, S, b0, np, nlev, start, goal, sdf);
     __syncthreads();
     const bool last = (j >= max_iters);
-    reduce_per_problem(S.nodes + N::oX, N::kStride, np, T, [&](int p, double s) {
-      if (!done[p] && !last && err_pi != nullptr) err_pi[(size_t)(b0 + p) * max_iters + j] = (IO)(s * invM);
-      if ((done[p] == 1 || last) && err_final != nullptr) err_final[b0 + p] = (IO)(s * invM);
-    });
-    reduce_per_problem(S.nodes + N::oX + 1, N::kStride, np, T, [&](int p, double s) {
-      if (!done[p] && !last && err_ext_pi != nullptr) err_ext_pi[(size_t)(b0 + p) * max_iters + j] = (IO)(s * invM);
-      if ((done[p] == 1 || last) && err_ext_final != nullptr) err_ext_final[b0 + p] = (IO)(s * invM);
+    reduce2_per_problem(S.nodes + N::oX, N::kStride, np, T, [&](int p, double s0, double s1) {
+      if (!done[p] && !last) {
+        if (err_pi != nullptr) err_pi[(size_t)(b0 + p) * max_iters + j] = (IO)(s0 * invM);
+        if (err_ext_pi != nullptr) err_ext_pi[(size_t)(b0 + p) * max_iters + j] = (IO)(s1 * invM);
+      }
+      if (done[p] == 1 || last) {
+        if (err_final != nullptr) err_final[b0 + p] = (IO)(s0 * invM);
+        if (err_ext_final != nullptr) err_ext_final[b0 + p] = (IO)(s1 * invM);
+      }
     });
     __syncthreads();
     // problems that converged at the previous iteration have now had their final error recorded
@@ -220,7 +267,7 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
     for (int p = 0; p < np; ++p) all_done = all_done && (done[p] == 2);
     if (all_done || last) break;
 
-    bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, P.wide_min, S.fail);
+    bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, P.wide_min, P.tail_max, S.fail);
 
     // th <- th + dth for problems still running; |dth|^2 partials
     for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
@@ -308,7 +355,7 @@ gn_step_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict_
   }
   __syncthreads();
 
-  bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, P.wide_min, S.fail);   // lambda in every record's [oR, oR+D)
+  bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, P.wide_min, P.tail_max, S.fail);   // lambda in every record's [oR, oR+D)
 
   const double invM = 1.0 / (double)P.M;
   const float inv_T = 1.0f / (float)T;

@@ -65,11 +65,17 @@ def _prep_w(t, dtype):
     return t if t.dtype == dtype else t.to(dtype)
 
 
-def gn_step(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, want_status=True):
-    """One batched GN iteration. Returns dth (B,T,d), err (B,), err_ext (B,), status (B,) int32 or None."""
+def gn_step(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, want_status=True, out=None):
+    """One batched GN iteration. Returns dth (B,T,d), err (B,), err_ext (B,), status (B,) int32 or None.
+    `out`: optional preallocated contiguous CUDA tensor (B,T,d) of th's dtype that receives dth."""
     th, start, goal, sdf = _common(p, th, start, goal, sdf)
     B, T, d = th.shape
-    dth = torch.empty_like(th)
+    if out is not None:
+        if out.shape != th.shape or out.dtype != th.dtype or not out.is_cuda or not out.is_contiguous():
+            raise ValueError('out must be a contiguous CUDA tensor with the shape and dtype of th')
+        dth = out
+    else:
+        dth = torch.empty_like(th)
     err = torch.empty(B, dtype=th.dtype, device=th.device)
     err_ext = torch.empty_like(err)
     status = torch.empty(B, dtype=torch.int32, device=th.device) if want_status else None

@@ -26,7 +26,7 @@ for l in range(1, 8):
     if a == 0: break
     print('level', l, 'elim', a-prev, 'kept', b-a)
     prev = b
-print('root', c[5]-prev)
+print('root', c[5]-prev, '(tail fwd', c[6]-prev, 'back', c[5]-c[6], ')')
 prev = c[5]
 for l in range(7, 0, -1):
     if c[40+l] == 0: continue

@@ -147,3 +147,24 @@ def test_forward_batch_vs_reference_golden():
         assert torch.isnan(epi[b, n:]).all()
     np.testing.assert_allclose(ef.cpu().numpy(), g['fwd_err_final'], rtol=1e-7)
     assert rel_err(th_final.cpu(), g['fwd_th_final']) < 1e-8
+
+
+@pytest.mark.parametrize('dof,T', [(2, 16), (3, 12)])
+def test_gn_step_output_pointer_alignment_does_not_matter(dof, T):
+    """The C ABI takes plain pointers: a dth buffer that is only element-aligned (here 4 bytes off a
+    16-byte boundary) must give the bits of an aligned one (wide stores are an internal fast path)."""
+    from dgpmp2_b200 import ops
+    from dgpmp2_b200.datasets.synthetic import make_problems
+    B, d = 5, 2 * dof
+    pr = make_problems(B, T, dof=dof, unique_envs=2, seed=3)
+    th, start, goal, sdf = (pr[k].cuda().float() for k in ('th_init', 'start', 'goal', 'sdf'))
+    from tests.gpu_helpers import cparams
+    from tests.helpers import XYH, YAML
+    cp = cparams(T, dof=dof, base=XYH if dof == 3 else YAML)
+    ref = ops.gn_step(cp, th, start, goal, sdf)
+    buf = torch.zeros(B * T * d + 8, dtype=torch.float32, device='cuda')
+    for off in (1, 2, 4):
+        out = buf[off:off + B * T * d].view(B, T, d)
+        got = ops.gn_step(cp, th, start, goal, sdf, out=out)
+        assert got[0].data_ptr() == buf.data_ptr() + 4 * off
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])

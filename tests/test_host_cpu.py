@@ -59,7 +59,7 @@ def test_launch_shape_and_limits():
     mk = lambda T, dof=2, B=1024: _lib.make_params(B, T, dof, 16, 16, (-5, 5), (-5, 5), 10.0, 0.4, 0.01, 0.01, 0.1, torch.eye(dof), 0.01, 0.4)
     s = ops.launch_shape(mk(64))
     # the ceil(1024 / 148) = 7 problems an SM has to process share ONE CTA (packed BCR items), 147 CTAs on 148 SMs
-    assert s['problems_per_cta'] == 7 and s['grid'] == 147 and s['threads'] == 512
+    assert s['problems_per_cta'] == 7 and s['grid'] == 147 and s['threads'] == 448
     assert s['smem_bytes'] <= 232448
     assert ops.launch_shape(mk(64, B=8))['problems_per_cta'] == 1   # small batches: one problem per CTA, 4 lanes per item
     assert ops.launch_shape(mk(64, B=8))['threads'] == 128
