@@ -47,41 +47,20 @@
 
 namespace dgpmp2 {
 
-constexpr int kMaxLevels = 16;
-constexpr int kLPN = 4;
-constexpr int kWideMinDefault = 64;   // work items in the CTA from which a level runs one lane per item
-constexpr int kTailMaxDefault = 4;    // elimination stops at this many nodes per problem; the rest is solved sequentially
-
-__host__ __device__ __forceinline__ int bcr_n_elim(int T, int s) { return (T + s - 1) / (2 * s); }   // nodes j = s(2q+1) < T
-__host__ __device__ __forceinline__ int bcr_n_kept(int T, int s) { return (T + 2 * s - 1) / (2 * s); } // nodes i = 2sq < T
-
-struct BcrLevels {
-  int nlev;                  // number of elimination levels (strides 1, 2, ... < T)
-  int off[kMaxLevels + 2];   // off[l] = first slot of level l (1-based); off[nlev+1] = T-1 = root slot
-};
-
-__host__ __device__ inline void bcr_make_levels(int T, BcrLevels& lv) {
-  lv.off[0] = 0;
-  lv.off[1] = 0;
-  int l = 1;
-  for (int s = 1; s < T; s <<= 1, ++l) lv.off[l + 1] = lv.off[l] + bcr_n_elim(T, s);
-  lv.nlev = l - 1;
-}
-
 // slot of trajectory state t inside its problem.  Closed form of off[l] + (t >> l) with
-// l = ctz(t) + 1 and off[l] = #{1 <= u < T : ctz(u) + 1 < l} = (T-1) - ((T-1) >> (l-1)); the table
-// argument is kept for the host-side / test model but not read on the device.
-__device__ __forceinline__ int bcr_slot(const int* /*off*/, int T, int t) {
+// l = ctz(t) + 1 and off[l] = #{1 <= u < T : ctz(u) + 1 < l} = (T-1) - ((T-1) >> (l-1)).
+__device__ __forceinline__ int bcr_slot(int T, int t) {
   const int z = __ffs(t) - 1;      // ctz(t); -1 for t == 0
   const int s = (T - 1) - ((T - 1) >> z) + (t >> (z + 1));
   return (t == 0) ? (T - 1) : s;
 }
-// inverse: trajectory state stored in slot m
-__device__ __forceinline__ int bcr_state_of_slot(const int* off, int nlev, int T, int m) {
+// inverse: trajectory state stored in slot m.  The level is the first l with off[l+1] > m.
+__device__ __forceinline__ int bcr_state_of_slot(int T, int m) {
   if (m == T - 1) return 0;
   int l = 1;
-  while (l < nlev && m >= off[l + 1]) ++l;
-  return (2 * (m - off[l]) + 1) << (l - 1);
+  while ((T - 1) - ((T - 1) >> l) <= m) ++l;
+  const int off = (T - 1) - ((T - 1) >> (l - 1));
+  return (2 * (m - off) + 1) << (l - 1);
 }
 
 template <int D>
@@ -209,14 +188,6 @@ struct LevelDiv {
     r = m - q * n;
   }
 };
-__device__ __forceinline__ LevelDiv make_level_div(int n) {
-  LevelDiv d;
-  d.n = n;
-  d.sh = ((n & (n - 1)) == 0) ? (__ffs(n) - 1) : -1;
-  d.inv = 1.0f / (float)n;
-  return d;
-}
-
 // ---------------------------------------------------------------------------------------------
 // The three per-level phases, templated on LPN = lanes per work item.
 //   LPN = 4: the lanes of an item split its columns / rows -> shortest dependent chain; used for the
@@ -230,14 +201,14 @@ __device__ __forceinline__ LevelDiv make_level_div(int n) {
 
 // (a) factor the eliminated nodes j = s(2e+1): L_j, E_j = L^-1 U_{j-s}^T, F_j = L^-1 U_j, g_j = L^-1 r_j
 template <int D, int LPN>
-__device__ __forceinline__ void bcr_elim_level(double* __restrict__ nodes, const int* __restrict__ lvl_off, int T, int np,
-                                               int s, int ne, int off_l, int* fail) {
+__device__ __forceinline__ void bcr_elim_level(double* __restrict__ nodes, int T, int np,
+                                               int s, const LevelDiv dv_e, int off_l, int* fail) {
   using N = Node<D>;
   constexpr int DS = N::DS, S = N::kStride;
   constexpr int NCL = (D + LPN - 1) / LPN;                             // columns per lane
   const int e0 = threadIdx.x / LPN, lane = threadIdx.x % LPN;
   const int EPP = blockDim.x / LPN;
-  const LevelDiv dv_e = make_level_div(ne);
+  const int ne = dv_e.n;
   for (int base = 0; base < np * ne; base += EPP) {   // uniform trip count for the whole CTA
     const int m = base + e0;
     const bool on = m < np * ne;
@@ -248,7 +219,7 @@ __device__ __forceinline__ void bcr_elim_level(double* __restrict__ nodes, const
       double* pn = nodes + (size_t)p * T * S;
       const int j = s * (2 * e + 1);
       double* nj = pn + (size_t)(off_l + e) * S;
-      const double* ni = pn + (size_t)bcr_slot(lvl_off, T, j - s) * S;
+      const double* ni = pn + (size_t)bcr_slot(T, j - s) * S;
       const bool has_right = (j + s) < T;
       double L[DS];
       ld_lower<D>(nj + N::oD, L);
@@ -317,20 +288,20 @@ __device__ __forceinline__ void bcr_elim_level(double* __restrict__ nodes, const
 // (b) Schur-complement update of the kept nodes i = 2se:
 //   D_i -= F_l^T F_l + E_r^T E_r,  r_i -= F_l^T g_l + E_r^T g_r,  U_i' = -E_r^T F_r   (l: j = i - s, r: j = i + s)
 template <int D, int LPN>
-__device__ __forceinline__ void bcr_kept_level(double* __restrict__ nodes, const int* __restrict__ lvl_off, int T, int np,
-                                               int s, int nk, int off_l) {
+__device__ __forceinline__ void bcr_kept_level(double* __restrict__ nodes, int T, int np,
+                                               int s, const LevelDiv dv_k, int off_l) {
   using N = Node<D>;
   constexpr int S = N::kStride;
   constexpr int NCL = (D + LPN - 1) / LPN;                             // rows per lane
   const int e0 = threadIdx.x / LPN, lane = threadIdx.x % LPN;
   const int EPP = blockDim.x / LPN;
-  const LevelDiv dv_k = make_level_div(nk);
+  const int nk = dv_k.n;
   for (int m = e0; m < np * nk; m += EPP) {
     int p, e;
     dv_k.split(m, p, e);
     double* pn = nodes + (size_t)p * T * S;
     const int i = 2 * s * e;
-    double* ni = pn + (size_t)bcr_slot(lvl_off, T, i) * S;
+    double* ni = pn + (size_t)bcr_slot(T, i) * S;
     const bool has_l = e > 0, has_r = (i + s) < T, has_rr = (i + 2 * s) < T;
     const double* nl = pn + (size_t)(off_l + (has_l ? e - 1 : 0)) * S;   // j = i - s
     const double* nr = pn + (size_t)(off_l + (has_r ? e : 0)) * S;       // j = i + s
@@ -429,14 +400,14 @@ __device__ __forceinline__ void bcr_kept_level(double* __restrict__ nodes, const
 
 // (c) back substitution of the nodes eliminated at this level: x_j = L_j^-T (g_j - E_j x_{j-s} - F_j x_{j+s})
 template <int D, int LPN>
-__device__ __forceinline__ void bcr_back_level(double* __restrict__ nodes, const int* __restrict__ lvl_off, int T, int np,
-                                               int s, int ne, int off_l) {
+__device__ __forceinline__ void bcr_back_level(double* __restrict__ nodes, int T, int np,
+                                               int s, const LevelDiv dv_e, int off_l) {
   using N = Node<D>;
   constexpr int DS = N::DS, S = N::kStride;
   constexpr int NCL = (D + LPN - 1) / LPN;                             // rows per lane
   const int e0 = threadIdx.x / LPN, lane = threadIdx.x % LPN;
   const int EPP = blockDim.x / LPN;
-  const LevelDiv dv_e = make_level_div(ne);
+  const int ne = dv_e.n;
   for (int base = 0; base < np * ne; base += EPP) {
     const int m = base + e0;
     const bool on = m < np * ne;
@@ -447,9 +418,9 @@ __device__ __forceinline__ void bcr_back_level(double* __restrict__ nodes, const
       double* pn = nodes + (size_t)p * T * S;
       const int j = s * (2 * e + 1);
       double* nj = pn + (size_t)(off_l + e) * S;
-      const double* ni = pn + (size_t)bcr_slot(lvl_off, T, j - s) * S;
+      const double* ni = pn + (size_t)bcr_slot(T, j - s) * S;
       const bool has_right = (j + s) < T;
-      const double* nk2 = has_right ? pn + (size_t)bcr_slot(lvl_off, T, j + s) * S : ni;
+      const double* nk2 = has_right ? pn + (size_t)bcr_slot(T, j + s) * S : ni;
       double xl[D], xr[D], L[DS];
       ld_vec<D>(ni + N::oR, xl);
       ld_vec<D>(nk2 + N::oR, xr);
@@ -521,7 +492,7 @@ __device__ __forceinline__ void bcr_back_level(double* __restrict__ nodes, const
 // exchange needed); the lanes only split the columns of F_e, which travel through the record.
 // With nc == 1 this is the classic root solve of cyclic reduction.
 template <int D>
-__device__ __forceinline__ void bcr_tail(double* __restrict__ nodes, const int* __restrict__ lvl_off, int T, int np,
+__device__ __forceinline__ void bcr_tail(double* __restrict__ nodes, int T, int np,
                                          int S_t, int nc, int* fail) {
   using N = Node<D>;
   constexpr int DS = N::DS, S = N::kStride, LPN = kLPN;
@@ -538,7 +509,7 @@ __device__ __forceinline__ void bcr_tail(double* __restrict__ nodes, const int* 
       const double* prev = pn;
 #pragma unroll 1
       for (int e = 0; e < nc; ++e) {
-        double* nd = pn + (size_t)bcr_slot(lvl_off, T, S_t * e) * S;
+        double* nd = pn + (size_t)bcr_slot(T, S_t * e) * S;
         const bool has_next = e + 1 < nc;
         double L[DS], r[D], vf[NCL][D];
         ld_lower<D>(nd + N::oD, L);
@@ -589,7 +560,7 @@ __device__ __forceinline__ void bcr_tail(double* __restrict__ nodes, const int* 
       for (int a = 0; a < D; ++a) x[a] = 0.0;
 #pragma unroll 1
       for (int e = nc - 1; e >= 0; --e) {
-        double* nd = pn + (size_t)bcr_slot(lvl_off, T, S_t * e) * S;
+        double* nd = pn + (size_t)bcr_slot(T, S_t * e) * S;
         double L[DS], v[D];
 #pragma unroll
         for (int k = 0; k < DS; k += 2) {
@@ -620,50 +591,49 @@ __device__ __forceinline__ void bcr_tail(double* __restrict__ nodes, const int* 
 // Factor + solve the CTA's np problems.  `nodes` = first record of problem 0 (np * T records,
 // problem-major).  The work items of a level are enumerated across ALL problems of the CTA
 // (item m -> problem m / n_items, node m % n_items) and packed onto consecutive lane groups, so
-// the sparse deep levels of several problems share warps.  A level with at least `wide_min` items
-// in the CTA runs one lane per item, the others kLPN lanes per item.  Elimination stops as soon as
-// at most `tail_max` nodes per problem are left; that chain is solved sequentially (bcr_tail).
+// the sparse deep levels of several problems share warps.  A level with at least plan.wide_min items
+// in the CTA runs one lane per item, the others kLPN lanes per item.  Elimination stops after
+// plan.nl levels; the remaining chain of plan.tail_nc nodes is solved sequentially (bcr_tail).
 // On exit every record's [oR, oR+D) holds x_t.  fail[p] (shared, pre-zeroed) receives t+1 of a node
 // of problem p whose pivot was not positive.  Must be called by ALL threads of the CTA (barriers).
 template <int D>
-__device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const int* __restrict__ lvl_off, int nlev,
-                                          int T, int np, int wide_min, int tail_max, int* fail) {
-  int nl = 0;                                 // elimination levels actually run (<= nlev)
-  while (((T + (1 << nl) - 1) >> nl) > tail_max) ++nl;
+__device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const BcrPlan& plan, int T, int np, int* fail) {
+  const int nl = plan.nl, wide_min = plan.wide_min;
 
   // ------------------------------ forward elimination ------------------------------
   int off_l = 0;
   for (int l = 1; l <= nl; ++l) {
     const int s = 1 << (l - 1);
-    const int ne = (T + s - 1) >> l;          // bcr_n_elim(T, s), 2s = 2^l
-    const int nk = (T + 2 * s - 1) >> l;      // bcr_n_kept(T, s)
-    const bool wide = np * ne >= wide_min;    // uniform
+    const BcrLevelPlan& lv = plan.lv[l - 1];
+    const LevelDiv dv_e = {lv.ne, lv.e_sh, lv.e_inv}, dv_k = {lv.nk, lv.k_sh, lv.k_inv};
+    const bool wide = np * lv.ne >= wide_min;    // uniform
     DGPMP2_REP(1, l)
-    if (wide) bcr_elim_level<D, 1>(nodes, lvl_off, T, np, s, ne, off_l, fail);
-    else      bcr_elim_level<D, kLPN>(nodes, lvl_off, T, np, s, ne, off_l, fail);
+    if (wide) bcr_elim_level<D, 1>(nodes, T, np, s, dv_e, off_l, fail);
+    else      bcr_elim_level<D, kLPN>(nodes, T, np, s, dv_e, off_l, fail);
     __syncthreads();
     DGPMP2_BCR_STAMP(8 + 2 * l);
     DGPMP2_REP(2, l)
-    if (wide) bcr_kept_level<D, 1>(nodes, lvl_off, T, np, s, nk, off_l);
-    else      bcr_kept_level<D, kLPN>(nodes, lvl_off, T, np, s, nk, off_l);
+    if (wide) bcr_kept_level<D, 1>(nodes, T, np, s, dv_k, off_l);
+    else      bcr_kept_level<D, kLPN>(nodes, T, np, s, dv_k, off_l);
     __syncthreads();
     DGPMP2_BCR_STAMP(9 + 2 * l);
-    off_l += ne;
+    off_l += lv.ne;
   }
 
   // ------------------------------ remaining chain (root when tail_max == 1) ------------------------------
-  bcr_tail<D>(nodes, lvl_off, T, np, 1 << nl, (T + (1 << nl) - 1) >> nl, fail);
+  bcr_tail<D>(nodes, T, np, plan.tail_stride, plan.tail_nc, fail);
   __syncthreads();
   DGPMP2_BCR_STAMP(5);
 
   // ------------------------------ back substitution ------------------------------
   for (int l = nl; l >= 1; --l) {
     const int s = 1 << (l - 1);
-    const int ne = (T + s - 1) >> l;
-    off_l -= ne;
+    const BcrLevelPlan& lv = plan.lv[l - 1];
+    const LevelDiv dv_e = {lv.ne, lv.e_sh, lv.e_inv};
+    off_l -= lv.ne;
     DGPMP2_REP(3, l)
-    if (np * ne >= wide_min) bcr_back_level<D, 1>(nodes, lvl_off, T, np, s, ne, off_l);
-    else                     bcr_back_level<D, kLPN>(nodes, lvl_off, T, np, s, ne, off_l);
+    if (np * lv.ne >= wide_min) bcr_back_level<D, 1>(nodes, T, np, s, dv_e, off_l);
+    else                        bcr_back_level<D, kLPN>(nodes, T, np, s, dv_e, off_l);
     __syncthreads();
     DGPMP2_BCR_STAMP(40 + l);
   }

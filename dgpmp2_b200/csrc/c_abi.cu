@@ -94,12 +94,7 @@ KParams make_kparams(const dgpmp2_params* p) {
     }
   k.static_gp = 0;   // set by the caller once the weights are known
   k.ext_same = 0;
-  BcrLevels lv;
-  bcr_make_levels(p->T, lv);
-  k.nlev = lv.nlev;
-  for (int l = 0; l < 18; ++l) k.lvl_off[l] = (l <= lv.nlev + 1) ? lv.off[l] : 0;
-  k.wide_min = env_int("DGPMP2_WIDE", kWideMinDefault);
-  k.tail_max = env_int("DGPMP2_TAIL", kTailMaxDefault);
+  bcr_make_plan(p->T, env_int("DGPMP2_TAIL", kTailMaxDefault), env_int("DGPMP2_WIDE", kWideMinDefault), k.plan);
   return k;
 }
 

@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "bcr_plan.cuh"
 
 namespace dgpmp2 {
 
@@ -34,11 +35,8 @@ struct KParams {
   double PQs[36];       // Phi^T Q^-1
   double PQPs[36];      // Phi^T Q^-1 Phi
   double Qf[36];        // Q^-1 from qc_fix (err_ext)
-  // BCR level table (bcr.cuh), computed on the host: lvl_off[l] = first node slot of level l
-  int nlev;
-  int lvl_off[18];
-  int tail_max;         // elimination stops once at most this many nodes per problem are left (bcr.cuh)
-  int wide_min;         // levels with at least this many work items in the CTA run one lane per item (bcr.cuh)
+  // BCR schedule (bcr.cuh: BcrPlan), computed on the host
+  BcrPlan plan;
 };
 
 template <typename IO>

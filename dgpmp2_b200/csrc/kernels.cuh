@@ -19,14 +19,13 @@ namespace dgpmp2 { __device__ void g_phase_clock_fwd(int i); }
 namespace dgpmp2 {
 
 // Shared-memory carve-up of the step / solve kernels: NP problems x T node records (bcr.cuh),
-// the staged trajectory, per-node |dth|^2 (solve kernel), the level table and per-problem flags.
+// the staged trajectory, per-node |dth|^2 (solve kernel) and per-problem flags.
 template <int D, typename IO>
 struct StepSmem {
   double* nodes;    // [NP*T] records of Node<D>::kStride doubles
   double* nrm;      // [NP*T] per-node |dth|^2 (solve kernel only)
   IO* th;           // [NP*T][D] staged trajectory, natural (problem, t, a) order
   IO* dth;          // [NP*T][D] staged forward step (backward kernel only)
-  int* lvl_off;     // [kMaxLevels + 2]
   int* fail;        // [NP]
   int* flags;       // [2*NP] solve kernel: converged flag per problem, then iteration count
   // mode: 0 = step, 1 = solve (adds nrm), 2 = backward (adds the dth stage)
@@ -36,7 +35,7 @@ struct StepSmem {
     if (mode == 1) b += NN * 8;
     b += NN * D * sizeof(IO) * (mode == 2 ? 2 : 1);
     b = (b + 15) & ~(size_t)15;
-    b += (kMaxLevels + 2) * 4 + (size_t)NP * 4 * 3 + 16;
+    b += (size_t)NP * 4 * 3 + 16;
     return b;
   }
   __device__ __forceinline__ void carve(unsigned char* raw, int NP, int T, int mode) {
@@ -48,8 +47,7 @@ struct StepSmem {
     th = reinterpret_cast<IO*>(nxt);
     dth = th + NN * D;
     size_t off = (reinterpret_cast<unsigned char*>(th + NN * D * (mode == 2 ? 2 : 1)) - raw + 15) & ~(size_t)15;
-    lvl_off = reinterpret_cast<int*>(raw + off);
-    fail = lvl_off + (kMaxLevels + 2);
+    fail = reinterpret_cast<int*>(raw + off);
     flags = fail + NP;
   }
 };
@@ -58,16 +56,16 @@ struct StepSmem {
 // in slot order) from the staged trajectory.
 template <int DOF, typename IO>
 __device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO>& Wt, const StepSmem<2 * DOF, IO>& S,
-                                             int b0, int np, int nlev,
+                                             int b0, int np,
                                              const IO* __restrict__ start, const IO* __restrict__ goal,
                                              const IO* __restrict__ sdf) {
   constexpr int D = 2 * DOF;
   using N = Node<D>;
   const int T = P.T;
-  const float inv_T = 1.0f / (float)T;
+  const float inv_T = P.plan.inv_T;
   for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
     const int p = fast_div(m, inv_T), slot = m - p * T;
-    const int t = bcr_state_of_slot(S.lvl_off, nlev, T, slot);
+    const int t = bcr_state_of_slot(T, slot);
     const int b = b0 + p;
     double thp[D], thc[D], thn[D];
     const IO* tp = S.th + ((size_t)p * T + t) * D;
@@ -150,7 +148,6 @@ __device__ __forceinline__ void store_state(IO* __restrict__ dst, const double (
 template <int D, typename IO>
 __device__ __forceinline__ void cta_prologue(const KParams& P, const StepSmem<D, IO>& S, int T, int NP, int np,
                                              const IO* __restrict__ th_src, bool solve) {
-  if (threadIdx.x < kMaxLevels + 2) S.lvl_off[threadIdx.x] = P.lvl_off[threadIdx.x];   // host-computed level table
   for (int p = threadIdx.x; p < NP; p += blockDim.x) {
     S.fail[p] = 0;
     if (solve) { S.flags[p] = 0; S.flags[NP + p] = 0; }
@@ -186,25 +183,24 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
 
   cta_prologue<D, IO>(P, S, T, NP, np, th + (size_t)b0 * T * D, false);
   __syncthreads();
-  const int nlev = P.nlev;
   DGPMP2_STAMP(1);
 
-  assemble_cta<DOF, IO>(P, Wt, S, b0, np, nlev, start, goal, sdf);
+  assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf);
   __syncthreads();
   DGPMP2_STAMP(2);
 
-  bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, P.wide_min, P.tail_max, S.fail);   // ends with a barrier
+  bcr_solve<D>(S.nodes, P.plan, T, np, S.fail);   // ends with a barrier
   DGPMP2_STAMP(3);
 
   {  // dth, natural order -> coalesced stores
     IO* dst = dth + (size_t)b0 * T * D;
     const int n = np * T;
-    const float inv_T = 1.0f / (float)T;
+    const float inv_T = P.plan.inv_T;
     const bool vec = (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0ull;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int p = fast_div(i, inv_T), t = i - p * T;
       double x[D];
-      ld_vec<D>(S.nodes + ((size_t)p * T + bcr_slot(S.lvl_off, T, t)) * N::kStride + N::oR, x);
+      ld_vec<D>(S.nodes + ((size_t)p * T + bcr_slot(T, t)) * N::kStride + N::oR, x);
       store_state<D, IO>(dst + (size_t)i * D, x, vec);
     }
   }
@@ -240,12 +236,11 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
 
   cta_prologue<D, IO>(P, S, T, NP, np, th_init + (size_t)b0 * T * D, true);
   __syncthreads();
-  const int nlev = P.nlev;
   const double invM = 1.0 / (double)P.M;
 
   for (int j = 0;; ++j) {
     // assemble at the current iterate; the errors at iterate j are a by-product
-    assemble_cta<DOF, IO>(P, Wt, S, b0, np, nlev, start, goal, sdf);
+    assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf);
     __syncthreads();
     const bool last = (j >= max_iters);
     reduce2_per_problem(S.nodes + N::oX, N::kStride, np, T, [&](int p, double s0, double s1) {
@@ -267,15 +262,15 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
     for (int p = 0; p < np; ++p) all_done = all_done && (done[p] == 2);
     if (all_done || last) break;
 
-    bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, P.wide_min, P.tail_max, S.fail);
+    bcr_solve<D>(S.nodes, P.plan, T, np, S.fail);
 
     // th <- th + dth for problems still running; |dth|^2 partials
     for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
-      const int p = m / T, t = m - p * T;
+      const int p = fast_div(m, P.plan.inv_T), t = m - p * T;
       double s2 = 0.0;
       if (!done[p]) {
         double x[D];
-        ld_vec<D>(S.nodes + ((size_t)p * T + bcr_slot(S.lvl_off, T, t)) * N::kStride + N::oR, x);
+        ld_vec<D>(S.nodes + ((size_t)p * T + bcr_slot(T, t)) * N::kStride + N::oR, x);
 #pragma unroll
         for (int a = 0; a < D; ++a) {
           // the reference adds dtheta (I/O dtype) to th (I/O dtype): round dth first, then add
@@ -337,15 +332,14 @@ gn_step_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict_
     for (int i = threadIdx.x; i < n; i += blockDim.x) S.dth[i] = __ldg(src + i);
   }
   __syncthreads();
-  const int nlev = P.nlev;
 
-  assemble_cta<DOF, IO>(P, Wt, S, b0, np, nlev, start, goal, sdf);
+  assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf);
   __syncthreads();
   {  // right-hand side := gbar (slot order)
-    const float inv_T = 1.0f / (float)T;
+    const float inv_T = P.plan.inv_T;
     for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
       const int p = fast_div(m, inv_T), slot = m - p * T;
-      const int t = bcr_state_of_slot(S.lvl_off, nlev, T, slot);
+      const int t = bcr_state_of_slot(T, slot);
       const IO* gp = g_dth + ((size_t)(b0 + p) * T + t) * D;
       double v[D];
 #pragma unroll
@@ -355,10 +349,10 @@ gn_step_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict_
   }
   __syncthreads();
 
-  bcr_solve<D>(S.nodes, S.lvl_off, nlev, T, np, P.wide_min, P.tail_max, S.fail);   // lambda in every record's [oR, oR+D)
+  bcr_solve<D>(S.nodes, P.plan, T, np, S.fail);   // lambda in every record's [oR, oR+D)
 
   const double invM = 1.0 / (double)P.M;
-  const float inv_T = 1.0f / (float)T;
+  const float inv_T = P.plan.inv_T;
   const int blk = (P.flags & FLAG_Q_FULL) ? D : DOF;
   for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
     const int p = fast_div(m, inv_T), t = m - p * T;
@@ -367,9 +361,9 @@ gn_step_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict_
     const IO* tp = S.th + ((size_t)p * T + t) * D;
     const IO* xp = S.dth + ((size_t)p * T + t) * D;
     const double* nb = S.nodes + (size_t)p * T * N::kStride;
-    ld_vec<D>(nb + (size_t)bcr_slot(S.lvl_off, T, t) * N::kStride + N::oR, lc);
-    if (t > 0) ld_vec<D>(nb + (size_t)bcr_slot(S.lvl_off, T, t - 1) * N::kStride + N::oR, lp);
-    if (t < T - 1) ld_vec<D>(nb + (size_t)bcr_slot(S.lvl_off, T, t + 1) * N::kStride + N::oR, ln);
+    ld_vec<D>(nb + (size_t)bcr_slot(T, t) * N::kStride + N::oR, lc);
+    if (t > 0) ld_vec<D>(nb + (size_t)bcr_slot(T, t - 1) * N::kStride + N::oR, lp);
+    if (t < T - 1) ld_vec<D>(nb + (size_t)bcr_slot(T, t + 1) * N::kStride + N::oR, ln);
 #pragma unroll
     for (int a = 0; a < D; ++a) {
       thc[a] = (double)tp[a]; dc[a] = (double)xp[a];

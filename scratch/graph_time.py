@@ -2,6 +2,8 @@
 import sys, os
 sys.path.insert(0, '/root/repo')
 import torch
+from dgpmp2_b200 import _lib
+if os.environ.get('DGPMP2_LIB'): _lib.LIB_PATH = os.environ['DGPMP2_LIB']
 from dgpmp2_b200 import ops
 from dgpmp2_b200.datasets.synthetic import make_problems
 from tests.gpu_helpers import cparams

@@ -2,7 +2,7 @@ import sys, ctypes, os
 sys.path.insert(0, '/root/repo')
 import torch
 from dgpmp2_b200 import _lib
-_lib.LIB_PATH = '/root/repo/scratch/libdgpmp2_timing.so'
+_lib.LIB_PATH = os.environ.get('DGPMP2_LIB', '/root/repo/scratch/libdgpmp2_timing.so')
 from dgpmp2_b200 import ops
 from dgpmp2_b200.datasets.synthetic import make_problems
 from tests.gpu_helpers import cparams
