@@ -406,15 +406,26 @@ def main():
     alg = algorithmic_bytes(B, T)
     kernel_us = ms / K * 1e3                   # this rank's average launch-to-launch duration of the one kernel in the step
     achieved = alg / (kernel_us * 1e-6) / 1e9
-    traffic = None
+    traffic, prof = None, {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get('dram_bytes_per_launch')
+        prof = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))
+        traffic = prof.get('dram_bytes_per_launch')
     except Exception:
         pass
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'kernel': 'gn_step_kernel<2,float>', 'kernel_us': kernel_us,
                 'algorithmic_bytes_per_launch': alg, 'peak_source': peak_src,
-                'note': 'latency-bound at this size: 3.2 MB per launch is 0.49 us at HBM peak (DESIGN.md, roofline)'}
+                'note': 'not HBM-bound at this size: 3.2 MB per launch is 0.49 us at HBM peak; the kernel is a chain of '
+                        'dependent fp64 block factorisations held in shared memory (DESIGN.md, roofline)'}
+    # second view: the fp64 pipe.  Instructions per launch come from the committed ncu capture, the peak is the
+    # DFMA issue rate measured on this GPU with three distinct register operands (profiles/r01_microbench.txt).
+    n64, pk64 = prof.get('fp64_warp_insts_per_launch'), prof.get('dfma_warp_insts_per_cycle_per_sm_measured')
+    if n64 and pk64:
+        sm_hz = 1e6 * float(((clocks or {}).get('sm_mhz') or (clocks or {}).get('sm_max_mhz') or 1965.0))
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
+        a64 = n64 / (kernel_us * 1e-6 * sm_hz * sms)
+        roofline['fp64_pipe'] = {'achieved': a64, 'peak': pk64, 'unit': 'fp64 warp-instructions/cycle/SM',
+                                 'frac': a64 / pk64, 'fp64_warp_insts_per_launch': n64}
 
     # ---------------- CPU baseline (oracle port of the reference algorithm) ----------------
     cpu = None

@@ -17,7 +17,7 @@ __global__ void k(int T, int nc, long long* cyc, double* out) {
   if (threadIdx.x < 8) fail[threadIdx.x] = 0;
   __syncthreads();
   long long t0 = clock64();
-  bcr_tail<4>(sm, nullptr, T, 1, 1, nc, fail);
+  bcr_tail<4>(sm, T, 1, 1, nc, fail);
   __syncthreads();
   long long t1 = clock64();
   if (threadIdx.x == 0) { cyc[0] = t1 - t0; out[0] = sm[N::oR] + fail[0]; }

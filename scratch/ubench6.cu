@@ -23,7 +23,7 @@ __global__ void k(int T, int nc, long long* cyc, double* out) {
 #pragma unroll 1
   for (int e = 0; e < nc; ++e) {
     long long t0 = clock64();
-    double* nd = sm + (size_t)bcr_slot(nullptr, T, e) * S;
+    double* nd = sm + (size_t)bcr_slot(T, e) * S;
     double L[DS], r[D], vf[D];
     ld_lower<D>(nd + N::oD, L);
     ld_vec<D>(nd + N::oR, r);
