@@ -26,10 +26,16 @@
 // records is bank-conflict free.
 //
 // Work decomposition.  The work items of a level (one node each) are enumerated across
-// all problems of the CTA and each is processed by LPN = 4 adjacent lanes that split its
-// columns (elimination), rows (Schur update) or rows of the right-hand side (back
-// substitution).  Lanes never exchange registers: everything goes through the records,
-// ordered by __syncwarp inside an item and by the two CTA barriers per level.
+// all problems of the CTA.  On the wide levels (>= plan.wide_min items in the CTA) one lane
+// handles one item: those levels are bound by the shared-memory pipe and one lane per item
+// halves the wavefronts.  On the narrow levels an item is processed by kLPN = 4 adjacent lanes
+// that split its columns (elimination), rows (Schur update) or rows of the right-hand side
+// (back substitution): those levels are bound by the dependent chain of one item.  Lanes never
+// exchange registers: everything goes through the records, ordered by __syncwarp inside an
+// item and by the two CTA barriers per level.  Once <= plan.tail_nc nodes per problem are
+// left, the chain is finished by sequential block Cholesky (bcr_tail) without CTA barriers.
+// Every multiply-add is an explicit fma / __dmul_rn / __dadd_rn, so all instantiations round
+// identically and a problem's result does not depend on its position in the batch.
 #pragma once
 #include "factors.cuh"
 
