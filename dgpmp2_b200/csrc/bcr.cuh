@@ -77,6 +77,11 @@ struct Node {
   static constexpr int oD = 0, oU = DD, oR = 2 * DD, oE = 2 * DD + D, oX = 3 * DD + D;
   static constexpr int kRaw = 3 * DD + D + 2;
   static constexpr int kStride = (kRaw % 4 == 2) ? kRaw : kRaw + 2;   // doubles; == 2 (mod 4) -> 12 (mod 32) words for D = 4, 6
+  // Records of consecutive problems are staggered by 16 bytes (4 banks): when T * kStride is a multiple of 32 words
+  // (every T that is a multiple of 8), lanes of different problems that read the same field of the same node would
+  // otherwise hit the same banks (the tail and the deepest levels mix problems inside a quarter-warp).
+  static constexpr int kProblemPad = 2;
+  __host__ __device__ static constexpr size_t problem_stride(int T) { return (size_t)T * kStride + kProblemPad; }
 };
 
 __device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
@@ -222,7 +227,7 @@ __device__ __forceinline__ void bcr_elim_level(double* __restrict__ nodes, int T
     if (on) {
       int p, e;
       dv_e.split(m, p, e);
-      double* pn = nodes + (size_t)p * T * S;
+      double* pn = nodes + (size_t)p * N::problem_stride(T);
       const int j = s * (2 * e + 1);
       double* nj = pn + (size_t)(off_l + e) * S;
       const double* ni = pn + (size_t)bcr_slot(T, j - s) * S;
@@ -305,7 +310,7 @@ __device__ __forceinline__ void bcr_kept_level(double* __restrict__ nodes, int T
   for (int m = e0; m < np * nk; m += EPP) {
     int p, e;
     dv_k.split(m, p, e);
-    double* pn = nodes + (size_t)p * T * S;
+    double* pn = nodes + (size_t)p * N::problem_stride(T);
     const int i = 2 * s * e;
     double* ni = pn + (size_t)bcr_slot(T, i) * S;
     const bool has_l = e > 0, has_r = (i + s) < T, has_rr = (i + 2 * s) < T;
@@ -421,7 +426,7 @@ __device__ __forceinline__ void bcr_back_level(double* __restrict__ nodes, int T
     if (on) {
       int p, e;
       dv_e.split(m, p, e);
-      double* pn = nodes + (size_t)p * T * S;
+      double* pn = nodes + (size_t)p * N::problem_stride(T);
       const int j = s * (2 * e + 1);
       double* nj = pn + (size_t)(off_l + e) * S;
       const double* ni = pn + (size_t)bcr_slot(T, j - s) * S;
@@ -510,7 +515,7 @@ __device__ __forceinline__ void bcr_tail(double* __restrict__ nodes, int T, int 
     const bool on = p < np;
     const unsigned m_t = __ballot_sync(0xffffffffu, on);
     if (on) {
-      double* pn = nodes + (size_t)p * T * S;
+      double* pn = nodes + (size_t)p * N::problem_stride(T);
       double gp[D];
       const double* prev = pn;
 #pragma unroll 1
@@ -518,8 +523,6 @@ __device__ __forceinline__ void bcr_tail(double* __restrict__ nodes, int T, int 
         double* nd = pn + (size_t)bcr_slot(T, S_t * e) * S;
         const bool has_next = e + 1 < nc;
         double L[DS], r[D], vf[NCL][D];
-        ld_lower<D>(nd + N::oD, L);
-        ld_vec<D>(nd + N::oR, r);
 #pragma unroll
         for (int q = 0; q < NCL; ++q) {
           const int c = lane + q * LPN;
@@ -529,17 +532,32 @@ __device__ __forceinline__ void bcr_tail(double* __restrict__ nodes, int T, int 
           }
         }
         if (e > 0) {
-          double F[D][D];                                              // F[c][k] = F_{e-1}(k, c)
+          // Schur update, split by rows over the lanes of the problem (it is fp64-issue bound: 14 dot products
+          // in one lane cost more than the Cholesky chain) and exchanged through the record itself
 #pragma unroll
-          for (int c = 0; c < D; ++c) ld_vec<D>(prev + N::oU + c * D, F[c]);
+          for (int q = 0; q < NCL; ++q) {
+            const int a = lane + q * LPN;
+            if (a < D) {
+              double drow[D], fa[D];
+              ld_vec<D>(nd + N::oD + a * D, drow);
+              double ra = nd[N::oR + a];
+              ld_vec<D>(prev + N::oU + a * D, fa);                     // column a of F_{e-1}
+              ra = __dsub_rn(ra, dot<D>(fa, gp));
 #pragma unroll
-          for (int a = 0; a < D; ++a) {
-            r[a] = __dsub_rn(r[a], dot<D>(F[a], gp));
-#pragma unroll
-            for (int c = 0; c <= a; ++c) L[tri(a, c)] = __dsub_rn(L[tri(a, c)], dot<D>(F[a], F[c]));
+              for (int c = 0; c < D; ++c) {
+                double fc[D];
+                ld_vec<D>(prev + N::oU + c * D, fc);
+                drow[c] = __dsub_rn(drow[c], dot<D>(fa, fc));
+              }
+              st_vec<D>(nd + N::oD + a * D, drow);
+              nd[N::oR + a] = ra;
+            }
           }
         }
-        __syncwarp(m_t);   // every lane of the problem has read U_e before it is overwritten by F_e
+        __syncwarp(m_t);   // rows of D_e', r_e' are published; every lane has read its column of U_e
+        ld_lower<D>(nd + N::oD, L);
+        ld_vec<D>(nd + N::oR, r);
+        __syncwarp(m_t);   // every lane holds D_e', r_e' before they are overwritten by L_e, g_e / F_e
         if (!chol_packed<D>(L)) atomicMax(&fail[p], S_t * e + 1);
         fwd_solve<D>(L, r);
 #pragma unroll

@@ -31,7 +31,7 @@ struct StepSmem {
   // mode: 0 = step, 1 = solve (adds nrm), 2 = backward (adds the dth stage)
   __host__ __device__ static size_t bytes(int NP, int T, int mode) {
     const size_t NN = (size_t)NP * T;
-    size_t b = NN * Node<D>::kStride * 8;
+    size_t b = (size_t)NP * Node<D>::problem_stride(T) * 8;
     if (mode == 1) b += NN * 8;
     b += NN * D * sizeof(IO) * (mode == 2 ? 2 : 1);
     b = (b + 15) & ~(size_t)15;
@@ -41,7 +41,7 @@ struct StepSmem {
   __device__ __forceinline__ void carve(unsigned char* raw, int NP, int T, int mode) {
     const size_t NN = (size_t)NP * T;
     nodes = reinterpret_cast<double*>(raw);
-    double* nxt = nodes + NN * Node<D>::kStride;
+    double* nxt = nodes + (size_t)NP * Node<D>::problem_stride(T);
     nrm = nxt;
     if (mode == 1) nxt += NN;
     th = reinterpret_cast<IO*>(nxt);
@@ -78,7 +78,7 @@ __device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO
     NodeOut<DOF> o;
     assemble_node<DOF, IO>(P, Wt, b, t, thp, thc, thn, start + (size_t)b * D, goal + (size_t)b * D,
                            sdf + (size_t)b * P.sdf_sb, o);
-    double* nd = S.nodes + (size_t)m * N::kStride;
+    double* nd = S.nodes + (size_t)p * N::problem_stride(T) + (size_t)slot * N::kStride;
 #pragma unroll
     for (int a = 0; a < D; ++a) {
       st_vec<D>(nd + N::oD + a * D, o.Dm[a]);
@@ -90,28 +90,28 @@ __device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO
 }
 
 // Deterministic per-problem reduction by warp w for problems w, w+nwarps, ...: sum over the T
-// values `base[(p*T + i) * stride]`.  `f(p, sum)` is called by lane 0.
+// values `base[p * pstride + i * stride]`.  `f(p, sum)` is called by lane 0.
 template <typename F>
-__device__ __forceinline__ void reduce_per_problem(const double* base, int stride, int np, int T, F f) {
+__device__ __forceinline__ void reduce_per_problem(const double* base, int stride, size_t pstride, int np, int T, F f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int p = warp; p < np; p += nwarps) {
     double s = 0.0;
-    for (int i = lane; i < T; i += 32) s += base[(size_t)(p * T + i) * stride];
+    for (int i = lane; i < T; i += 32) s += base[(size_t)p * pstride + (size_t)i * stride];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) f(p, s);
   }
 }
 
-// Same for two interleaved quantities stored as adjacent doubles (16-byte aligned): `base[(p*T + i) * stride + {0, 1}]`.
+// Same for two interleaved quantities stored as adjacent doubles (16-byte aligned): `base[p * pstride + i * stride + {0, 1}]`.
 // Each component is summed in exactly the order reduce_per_problem uses.  `f(p, sum0, sum1)` is called by lane 0.
 template <typename F>
-__device__ __forceinline__ void reduce2_per_problem(const double* base, int stride, int np, int T, F f) {
+__device__ __forceinline__ void reduce2_per_problem(const double* base, int stride, size_t pstride, int np, int T, F f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int p = warp; p < np; p += nwarps) {
     double s0 = 0.0, s1 = 0.0;
     for (int i = lane; i < T; i += 32) {
-      const double2 v = lds2(base + (size_t)(p * T + i) * stride);
+      const double2 v = lds2(base + (size_t)p * pstride + (size_t)i * stride);
       s0 += v.x;
       s1 += v.y;
     }
@@ -200,12 +200,12 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int p = fast_div(i, inv_T), t = i - p * T;
       double x[D];
-      ld_vec<D>(S.nodes + ((size_t)p * T + bcr_slot(T, t)) * N::kStride + N::oR, x);
+      ld_vec<D>(S.nodes + (size_t)p * N::problem_stride(T) + (size_t)bcr_slot(T, t) * N::kStride + N::oR, x);
       store_state<D, IO>(dst + (size_t)i * D, x, vec);
     }
   }
   const double invM = 1.0 / (double)P.M;
-  reduce2_per_problem(S.nodes + N::oX, N::kStride, np, T, [&](int p, double s0, double s1) {
+  reduce2_per_problem(S.nodes + N::oX, N::kStride, N::problem_stride(T), np, T, [&](int p, double s0, double s1) {
     err[b0 + p] = (IO)(s0 * invM);
     err_ext[b0 + p] = (IO)(s1 * invM);
   });
@@ -243,7 +243,7 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
     assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf);
     __syncthreads();
     const bool last = (j >= max_iters);
-    reduce2_per_problem(S.nodes + N::oX, N::kStride, np, T, [&](int p, double s0, double s1) {
+    reduce2_per_problem(S.nodes + N::oX, N::kStride, N::problem_stride(T), np, T, [&](int p, double s0, double s1) {
       if (!done[p] && !last) {
         if (err_pi != nullptr) err_pi[(size_t)(b0 + p) * max_iters + j] = (IO)(s0 * invM);
         if (err_ext_pi != nullptr) err_ext_pi[(size_t)(b0 + p) * max_iters + j] = (IO)(s1 * invM);
@@ -270,7 +270,7 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
       double s2 = 0.0;
       if (!done[p]) {
         double x[D];
-        ld_vec<D>(S.nodes + ((size_t)p * T + bcr_slot(T, t)) * N::kStride + N::oR, x);
+        ld_vec<D>(S.nodes + (size_t)p * N::problem_stride(T) + (size_t)bcr_slot(T, t) * N::kStride + N::oR, x);
 #pragma unroll
         for (int a = 0; a < D; ++a) {
           // the reference adds dtheta (I/O dtype) to th (I/O dtype): round dth first, then add
@@ -283,7 +283,7 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
       S.nrm[m] = s2;
     }
     __syncthreads();
-    reduce_per_problem(S.nrm, 1, np, T, [&](int p, double s) {
+    reduce_per_problem(S.nrm, 1, (size_t)T, np, T, [&](int p, double s) {
       if (!done[p]) {
         nit[p] = j + 1;
         // check_convergence (planner_utils.py:3-16): ||dtheta|| < tol_delta  or  j+1 >= max_iters
@@ -344,7 +344,7 @@ gn_step_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict_
       double v[D];
 #pragma unroll
       for (int a = 0; a < D; ++a) v[a] = ldg_d(gp + a);
-      st_vec<D>(S.nodes + (size_t)m * N::kStride + N::oR, v);
+      st_vec<D>(S.nodes + (size_t)p * N::problem_stride(T) + (size_t)slot * N::kStride + N::oR, v);
     }
   }
   __syncthreads();
@@ -360,7 +360,7 @@ gn_step_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict_
     double thp[D], thc[D], thn[D], lp[D], lc[D], ln[D], dp[D], dc[D], dn[D];
     const IO* tp = S.th + ((size_t)p * T + t) * D;
     const IO* xp = S.dth + ((size_t)p * T + t) * D;
-    const double* nb = S.nodes + (size_t)p * T * N::kStride;
+    const double* nb = S.nodes + (size_t)p * N::problem_stride(T);
     ld_vec<D>(nb + (size_t)bcr_slot(T, t) * N::kStride + N::oR, lc);
     if (t > 0) ld_vec<D>(nb + (size_t)bcr_slot(T, t - 1) * N::kStride + N::oR, lp);
     if (t < T - 1) ld_vec<D>(nb + (size_t)bcr_slot(T, t + 1) * N::kStride + N::oR, ln);
