@@ -32,7 +32,7 @@ struct StepSmem {
   __host__ __device__ static size_t bytes(int NP, int T, int mode) {
     const size_t NN = (size_t)NP * T;
     size_t b = (size_t)NP * Node<D>::problem_stride(T) * 8;
-    if (mode == 1) b += NN * 8;
+    if (mode == 1) b += ((NN + 1) & ~(size_t)1) * 8;   // keeps the staged trajectory 16-byte aligned
     b += NN * D * sizeof(IO) * (mode == 2 ? 2 : 1);
     b = (b + 15) & ~(size_t)15;
     b += (size_t)NP * 4 * 3 + 16;
@@ -43,7 +43,7 @@ struct StepSmem {
     nodes = reinterpret_cast<double*>(raw);
     double* nxt = nodes + (size_t)NP * Node<D>::problem_stride(T);
     nrm = nxt;
-    if (mode == 1) nxt += NN;
+    if (mode == 1) nxt += (NN + 1) & ~(size_t)1;
     th = reinterpret_cast<IO*>(nxt);
     dth = th + NN * D;
     size_t off = (reinterpret_cast<unsigned char*>(th + NN * D * (mode == 2 ? 2 : 1)) - raw + 15) & ~(size_t)15;
