@@ -1,7 +1,8 @@
 """Executable numpy model of the kernel's block cyclic reduction (dgpmp2_b200/csrc/bcr.cuh).
 
-Mirrors the CUDA code item for item (level-ordered slots, E/F/g storage, kept-node
-updates, back substitution) so the index algebra can be validated on the CPU.
+Mirrors the CUDA code item for item (level-ordered slots and their closed forms, E/F/g
+storage, kept-node updates, the block-Thomas tail, back substitution) so the index algebra
+can be validated on the CPU.
 Test infrastructure only.
 """
 import numpy as np
@@ -40,20 +41,50 @@ def state_of_slot(off, nlev, T, m):
     return (2 * (m - off[l]) + 1) << (l - 1)
 
 
-def bcr_solve(D, U, r):
-    """D (T,d,d) SPD diagonal blocks, U (T-1,d,d) = Lambda[t,t+1], r (T,d) -> x (T,d)."""
+def slot_closed_form(T, t):
+    """bcr_slot of bcr.cuh: off[l] = (T-1) - ((T-1) >> (l-1)) with l = ctz(t) + 1."""
+    if t == 0:
+        return T - 1
+    z = (t & -t).bit_length() - 1
+    return (T - 1) - ((T - 1) >> z) + (t >> (z + 1))
+
+
+def state_of_slot_closed_form(T, m):
+    """bcr_state_of_slot of bcr.cuh."""
+    if m == T - 1:
+        return 0
+    l = 1
+    while (T - 1) - ((T - 1) >> l) <= m:
+        l += 1
+    off = (T - 1) - ((T - 1) >> (l - 1))
+    return (2 * (m - off) + 1) << (l - 1)
+
+
+def make_plan(T, tail_max=4):
+    """bcr_make_plan of bcr_plan.cuh: levels run, stride and length of the chain left for the tail."""
+    nl = 0
+    while ((T + (1 << nl) - 1) >> nl) > tail_max:
+        nl += 1
+    return nl, 1 << nl, (T + (1 << nl) - 1) >> nl
+
+
+def bcr_solve(D, U, r, tail_max=4):
+    """D (T,d,d) SPD diagonal blocks, U (T-1,d,d) = Lambda[t,t+1], r (T,d) -> x (T,d).
+    nl elimination levels, then the block-Thomas tail on the chain t = S e (bcr_tail), then back substitution."""
     T, d, _ = D.shape
     nlev, off = make_levels(T)
+    nl, S_t, nc = make_plan(T, tail_max)
+    assert nl <= nlev and nc <= max(tail_max, 1) and (nc - 1) * S_t < T <= nc * S_t
     Dm = np.zeros((T, d, d)); Um = np.zeros((T, d, d)); Rm = np.zeros((T, d)); Em = np.zeros((T, d, d))
     Lm = [None] * T
     for m in range(T):
         t = state_of_slot(off, nlev, T, m)
-        assert slot(off, T, t) == m
+        assert slot(off, T, t) == m == slot_closed_form(T, t) and state_of_slot_closed_form(T, m) == t
         Dm[m] = D[t]
         if t < T - 1:
             Um[m] = U[t]
         Rm[m] = r[t]
-    for l in range(1, nlev + 1):
+    for l in range(1, nl + 1):
         s = 1 << (l - 1)
         ne = n_elim(T, s)
         for q in range(ne):
@@ -81,9 +112,26 @@ def bcr_solve(D, U, r):
                 Rm[pi] -= Em[pr].T @ Rm[pr]
             if (i + 2 * s) < T:
                 Um[pi] = -Em[pr].T @ Um[pr]
-    p0 = T - 1
-    Rm[p0] = np.linalg.solve(Dm[p0], Rm[p0])
-    for l in range(nlev, 0, -1):
+    # tail: sequential block Cholesky over the chain t = S_t e, e = 0..nc-1 (root solve when nc == 1)
+    prev = None
+    for e in range(nc):
+        pe = slot(off, T, S_t * e)
+        if prev is not None:
+            Dm[pe] -= Um[prev].T @ Um[prev]
+            Rm[pe] -= Um[prev].T @ Rm[prev]
+        L = np.linalg.cholesky(Dm[pe])
+        Lm[pe] = L
+        if e + 1 < nc:
+            Um[pe] = np.linalg.solve(L, Um[pe])
+        Rm[pe] = np.linalg.solve(L, Rm[pe])
+        prev = pe
+    xn = None
+    for e in range(nc - 1, -1, -1):
+        pe = slot(off, T, S_t * e)
+        v = Rm[pe] if xn is None else Rm[pe] - Um[pe] @ xn
+        Rm[pe] = np.linalg.solve(Lm[pe].T, v)
+        xn = Rm[pe]
+    for l in range(nl, 0, -1):
         s = 1 << (l - 1)
         for q in range(n_elim(T, s)):
             j = s * (2 * q + 1)

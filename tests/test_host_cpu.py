@@ -176,7 +176,7 @@ def test_synthetic_problem_generator_is_deterministic():
 def test_bcr_numpy_model_matches_dense_solve():
     from tests.bcr_model import bcr_solve
     rng = np.random.default_rng(0)
-    for T, d in [(2, 4), (5, 4), (64, 4), (96, 6), (101, 4)]:
+    for T, d in [(2, 4), (3, 4), (5, 4), (8, 4), (9, 4), (64, 4), (96, 6), (101, 4), (128, 4)]:
         N = T * d
         A = np.zeros((N, N))
         U = rng.standard_normal((T - 1, d, d))
@@ -185,5 +185,7 @@ def test_bcr_numpy_model_matches_dense_solve():
         A = A + A.T + np.eye(N) * 30.0
         D = np.stack([A[t * d:(t + 1) * d, t * d:(t + 1) * d] for t in range(T)])
         r = rng.standard_normal((T, d))
-        x = bcr_solve(D, U, r)
-        assert np.abs(x - np.linalg.solve(A, r.reshape(-1)).reshape(T, d)).max() < 1e-12
+        ref = np.linalg.solve(A, r.reshape(-1)).reshape(T, d)
+        for tail_max in (1, 2, 4, 8):      # 1 = classic root solve; 4 = the kernel's default
+            x = bcr_solve(D, U, r, tail_max=tail_max)
+            assert np.abs(x - ref).max() < 1e-12, (T, d, tail_max)
