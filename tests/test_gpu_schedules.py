@@ -1,0 +1,70 @@
+"""-m gpu: the solver across trajectory lengths, batch sizes and elimination schedules.
+
+Every problem's dtheta must satisfy its own normal equations (band kernel, fp64) to rounding, for ragged T
+(non powers of two, shorter than the tail, longer than a level), 1 / several / many problems per CTA, and with
+the schedule knobs forced so that the one-lane levels, the 4-lane levels, multi-problem item packing and tails of
+length 1..7 are all exercised on small problems.  The knobs are the library's documented debug overrides
+(DGPMP2_WIDE / DGPMP2_NP / DGPMP2_TAIL, read per call in c_abi.cu)."""
+import os
+
+import pytest
+import torch
+
+from tests.helpers import XYH, YAML
+
+pytestmark = pytest.mark.gpu
+
+SCHEDULES = [{}, {'DGPMP2_WIDE': '4'}, {'DGPMP2_WIDE': '4', 'DGPMP2_NP': '3'}, {'DGPMP2_TAIL': '1'},
+             {'DGPMP2_TAIL': '7', 'DGPMP2_NP': '5'}]
+KNOBS = ('DGPMP2_WIDE', 'DGPMP2_NP', 'DGPMP2_TAIL')
+
+
+def _band_matvec(D, U, x):
+    y = torch.einsum('btij,btj->bti', D, x)
+    y[:, :-1] += torch.einsum('btij,btj->bti', U, x[:, 1:])
+    y[:, 1:] += torch.einsum('btji,btj->bti', U, x[:, :-1])
+    return y
+
+
+@pytest.mark.parametrize('dof', [2, 3])
+@pytest.mark.parametrize('sched', SCHEDULES, ids=lambda s: '-'.join('%s%s' % (k[7:], v) for k, v in s.items()) or 'default')
+def test_every_problem_solves_its_normal_equations(sched, dof):
+    from dgpmp2_b200 import ops
+    from dgpmp2_b200.datasets.synthetic import make_problems
+    from tests.gpu_helpers import cparams
+    saved = {k: os.environ.pop(k, None) for k in KNOBS}
+    os.environ.update(sched)
+    try:
+        base = XYH if dof == 3 else YAML
+        ref = {}
+        for T in (2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 33, 64, 65, 101, 128):
+            for B in (1, 7, 150):
+                pr = make_problems(B, T, dof=dof, unique_envs=3, seed=T * 7 + B, im_size=48)
+                th, start, goal, sdf = (pr[k].cuda().double() for k in ('th_init', 'start', 'goal', 'sdf'))
+                th = th + 0.05 * torch.randn(th.shape, generator=torch.Generator().manual_seed(T)).cuda().double()
+                cp = cparams(T, base=base, dof=dof, non_holonomic=(dof == 3))
+                dth, err, err_ext, status = ops.gn_step(cp, th, start, goal, sdf)
+                assert int(status.abs().max()) == 0 and bool(torch.isfinite(dth).all()), (T, B)
+                D, U, r = ops.band(cp, th, start, goal, sdf)
+                res = _band_matvec(D, U, dth) - r
+                lam = (D.reshape(B, -1).norm(dim=1) ** 2 + 2 * U.reshape(B, -1).norm(dim=1) ** 2).sqrt()
+                eta = (res.reshape(B, -1).norm(dim=1) /
+                       (lam * dth.reshape(B, -1).norm(dim=1) + r.reshape(B, -1).norm(dim=1))).max().item()
+                assert eta < 1e-13, (T, B, eta)      # normwise backward error: independent of cond(Lambda)
+                ref[(T, B)] = dth
+        if sched.get('DGPMP2_WIDE') == '4' and 'DGPMP2_NP' not in sched:
+            # one lane per item vs four lanes per item: same bits (explicit-fma arithmetic)
+            os.environ['DGPMP2_WIDE'] = '100000'
+            for (T, B), d0 in ref.items():
+                if B != 7 or T not in (16, 64, 101):
+                    continue
+                pr = make_problems(B, T, dof=dof, unique_envs=3, seed=T * 7 + B, im_size=48)
+                th, start, goal, sdf = (pr[k].cuda().double() for k in ('th_init', 'start', 'goal', 'sdf'))
+                th = th + 0.05 * torch.randn(th.shape, generator=torch.Generator().manual_seed(T)).cuda().double()
+                cp = cparams(T, base=base, dof=dof, non_holonomic=(dof == 3))
+                assert torch.equal(ops.gn_step(cp, th, start, goal, sdf)[0], d0), (T, B)
+    finally:
+        for k in KNOBS:
+            os.environ.pop(k, None)
+            if saved[k] is not None:
+                os.environ[k] = saved[k]
