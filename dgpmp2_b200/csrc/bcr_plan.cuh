@@ -8,7 +8,7 @@ namespace dgpmp2 {
 
 constexpr int kMaxLevels = 16;
 constexpr int kLPN = 4;               // lanes per work item on the narrow levels
-constexpr int kWideMinDefault = 64;   // work items in the CTA from which a level runs one lane per item
+constexpr int kWideMinDefault = 56;   // work items in the CTA from which a level runs one lane per item
 constexpr int kTailMaxDefault = 4;    // elimination stops at this many nodes per problem; the rest is solved sequentially
 
 __host__ __device__ __forceinline__ int bcr_n_elim(int T, int s) { return (T + s - 1) / (2 * s); }   // nodes j = s(2q+1) < T
