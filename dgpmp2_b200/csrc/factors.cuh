@@ -66,12 +66,12 @@ __device__ __forceinline__ SdfSample sdf_bilinear(const IO* __restrict__ sdf, in
   // px = orig_x + x / res ; py = orig_y - y / res   (true divisions, reference order)
   const double px = __dadd_rn(orig_x, __ddiv_rn(x, res));
   const double py = __dsub_rn(orig_y, __ddiv_rn(y, res));
-  const double fx = floor(px), fy = floor(py);
-  // floor -> +1 -> clamp to the image (sdf_utils.py:64-72), done in double so huge values cannot overflow
-  const double wm = (double)(W - 1), hm = (double)(H - 1);
-  const double x1d = fmin(fmax(fx, 0.0), wm), x2d = fmin(fmax(fx + 1.0, 0.0), wm);
-  const double y1d = fmin(fmax(fy, 0.0), hm), y2d = fmin(fmax(fy + 1.0, 0.0), hm);
-  const int x1 = (int)x1d, x2 = (int)x2d, y1 = (int)y1d, y2 = (int)y2d;
+  // floor -> +1 -> clamp to the image (sdf_utils.py:64-72).  The clamps run on integers: cvt.rmi saturates, so
+  // |px| >= 2^31 lands on the same border pixel as the reference's float clamp (a NaN coordinate gives NaN either way)
+  const int ix = __double2int_rd(px), iy = __double2int_rd(py);
+  const int x1 = min(max(ix, 0), W - 1), x2 = min(max(ix, -1), W - 2) + 1;   // clamp(ix + 1, 0, W - 1) without overflow
+  const int y1 = min(max(iy, 0), H - 1), y2 = min(max(iy, -1), H - 2) + 1;
+  const double x1d = (double)x1, x2d = (double)x2, y1d = (double)y1, y2d = (double)y2;
   const IO* r1 = sdf + (long long)y1 * W;
   const IO* r2 = sdf + (long long)y2 * W;
   const double v11 = ldg_d(r1 + x1), v21 = ldg_d(r1 + x2);
