@@ -482,12 +482,8 @@ __device__ __forceinline__ void bcr_back_level(double* __restrict__ nodes, int T
         double v[D];
         ld_vec<D>(nj + N::oR, v);
         bwd_solve<D>(L, v);
-        __syncwarp(m_bs);   // all lanes have read v before any lane overwrites it with x_j
-#pragma unroll
-        for (int q = 0; q < NCL; ++q) {
-          const int a = lane + q * LPN;
-          if (a < D) nj[N::oR + a] = v[a];
-        }
+        __syncwarp(m_bs);   // all lanes have read v before it is overwritten with x_j
+        if (lane == 0) st_vec<D>(nj + N::oR, v);   // (indexing v[] by the lane would put it in local memory)
       }
     }
   }

@@ -189,3 +189,17 @@ def test_bcr_numpy_model_matches_dense_solve():
         for tail_max in (1, 2, 4, 8):      # 1 = classic root solve; 4 = the kernel's default
             x = bcr_solve(D, U, r, tail_max=tail_max)
             assert np.abs(x - ref).max() < 1e-12, (T, d, tail_max)
+
+
+def test_slot_maps_closed_forms_are_inverse_bijections():
+    """bcr_slot / bcr_state_of_slot (closed forms used on the device) against the level-table definition."""
+    from tests.bcr_model import make_levels, slot, slot_closed_form, state_of_slot, state_of_slot_closed_form
+    for T in list(range(2, 140)) + [255, 256, 257, 500, 518]:
+        nlev, off = make_levels(T)
+        seen = set()
+        for t_ in range(T):
+            m = slot_closed_form(T, t_)
+            assert m == slot(off, T, t_) and 0 <= m < T
+            assert state_of_slot_closed_form(T, m) == t_ == state_of_slot(off, nlev, T, m)
+            seen.add(m)
+        assert len(seen) == T
