@@ -17,6 +17,9 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libdgpmp2_b200.so')
 FLAG_NONHOLONOMIC = 1
 FLAG_VEL_LIMITS = 2
 FLAG_Q_FULL = 4
+FLAG_HEAD = 8            # weights hold the raw outputs of the learned module (fused get_covariances)
+FLAG_HEAD_QC_VEC = 16    # ... and Qc^-1 = v v^T from dof values ('qc_full'); alone: q^2 I ('diag_identity')
+HEAD_MODES = ('fix_dynamics', 'diag_identity', 'qc_full', 'q_full')
 
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 
@@ -250,4 +253,52 @@ def make_weights(qc_inv: Optional[torch.Tensor], w_obs: Optional[torch.Tensor], 
         w.w_obs, w.w_stride_b, w.w_stride_t = scalar_field(w_obs, 'obscov_inv')
     if eps is not None:
         w.eps, w.eps_stride_b, w.eps_stride_t = scalar_field(eps, 'eps')
+    return w, keep
+
+
+def head_block(mode: str, dof: int) -> int:
+    """Raw values per GP factor in the learned module's output (diff_gpmp2_planner.py:250-278)."""
+    if mode not in HEAD_MODES:
+        raise NotImplementedError('dynamics_mode %r' % (mode,))
+    return {'fix_dynamics': 0, 'diag_identity': 1, 'qc_full': dof, 'q_full': 2 * dof}[mode]
+
+
+def set_head_flags(p: CParams, mode: str):
+    """Select the fused covariance head of the kernels for this call (DGPMP2_FLAG_HEAD*)."""
+    head_block(mode, p.dof)
+    if (mode == 'q_full') != bool(p.flags & FLAG_Q_FULL):
+        raise ValueError("dynamics_mode 'q_full' needs params built with q_full=True (and only that mode does)")
+    p.flags |= FLAG_HEAD
+    if mode == 'qc_full':
+        p.flags |= FLAG_HEAD_QC_VEC
+
+
+def make_head_weights(q_raw: Optional[torch.Tensor], o_raw: Optional[torch.Tensor], e_raw: Optional[torch.Tensor],
+                      B: int, T: int, n: int):
+    """struct dgpmp2_weights over RAW head outputs (views of the learned module's ``out``; no copies):
+    q_raw (B|1, T-1|1, n) with n values per GP factor, o_raw / e_raw (B|1, T|1)."""
+    w = CWeights()
+    keep = []
+    if q_raw is not None:
+        q = q_raw
+        if q.dim() != 3 or q.shape[2] != n or q.shape[0] not in (1, B) or q.shape[1] not in (1, T - 1):
+            raise ValueError('raw Qc head output must be (B,T-1,%d), got %s' % (n, tuple(q_raw.shape)))
+        if n > 1 and q.stride(2) != 1:
+            q = q.contiguous()
+        keep.append(q)
+        w.qc_inv = q.data_ptr()
+        w.qc_stride_b = 0 if q.shape[0] == 1 else q.stride(0)
+        w.qc_stride_t = 0 if q.shape[1] == 1 else q.stride(1)
+    for name, t in (('w_obs', o_raw), ('eps', e_raw)):
+        if t is None:
+            continue
+        if t.dim() != 2 or t.shape[0] not in (1, B) or t.shape[1] not in (1, T):
+            raise ValueError('raw %s head output must be (B,T), got %s' % (name, tuple(t.shape)))
+        keep.append(t)
+        sb = 0 if t.shape[0] == 1 else t.stride(0)
+        st = 0 if t.shape[1] == 1 else t.stride(1)
+        if name == 'w_obs':
+            w.w_obs, w.w_stride_b, w.w_stride_t = t.data_ptr(), sb, st
+        else:
+            w.eps, w.eps_stride_b, w.eps_stride_t = t.data_ptr(), sb, st
     return w, keep

@@ -29,7 +29,10 @@ int check_params(const dgpmp2_params* p, const dgpmp2_weights* w) {
   if (p == nullptr) return DGPMP2_ERR_ARG;
   if (p->B < 0 || p->T < 2 || p->H < 1 || p->W < 1) return DGPMP2_ERR_ARG;
   if (p->dof != 2 && p->dof != 3) return DGPMP2_ERR_UNSUPPORTED;
-  if (p->flags & ~(DGPMP2_FLAG_NONHOLONOMIC | DGPMP2_FLAG_VEL_LIMITS | DGPMP2_FLAG_Q_FULL)) return DGPMP2_ERR_ARG;
+  if (p->flags & ~(DGPMP2_FLAG_NONHOLONOMIC | DGPMP2_FLAG_VEL_LIMITS | DGPMP2_FLAG_Q_FULL | DGPMP2_FLAG_HEAD |
+                   DGPMP2_FLAG_HEAD_QC_VEC)) return DGPMP2_ERR_ARG;
+  if ((p->flags & DGPMP2_FLAG_HEAD_QC_VEC) && !(p->flags & DGPMP2_FLAG_HEAD)) return DGPMP2_ERR_ARG;
+  if ((p->flags & DGPMP2_FLAG_HEAD) && w == nullptr) return DGPMP2_ERR_ARG;   // a head without outputs
   if ((p->flags & DGPMP2_FLAG_NONHOLONOMIC) && (p->flags & DGPMP2_FLAG_VEL_LIMITS)) return DGPMP2_ERR_ARG;
   if ((p->flags & DGPMP2_FLAG_NONHOLONOMIC) && p->dof != 3) return DGPMP2_ERR_ARG;
   if ((p->flags & DGPMP2_FLAG_VEL_LIMITS) && p->dof != 2) return DGPMP2_ERR_ARG;

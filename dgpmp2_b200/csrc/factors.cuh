@@ -46,11 +46,28 @@ struct KWeights {
   const IO* eps; long long e_sb, e_st;
 };
 
-enum : int { FLAG_NONHOLONOMIC = 1, FLAG_VEL_LIMITS = 2, FLAG_Q_FULL = 4 };
+enum : int { FLAG_NONHOLONOMIC = 1, FLAG_VEL_LIMITS = 2, FLAG_Q_FULL = 4, FLAG_HEAD = 8, FLAG_HEAD_QC_VEC = 16 };
 
 __device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
 
 template <typename IO> __device__ __forceinline__ double ldg_d(const IO* p) { return (double)__ldg(p); }
+
+// ---------------------------------------------------------------------------
+// Fused learned-covariance head (diff_gpmp2_planner.py:247-283).  With FLAG_HEAD the weight pointers hold
+// the raw outputs of the learned module; every covariance entry is a product of two of them, rounded once in
+// the I/O element type (what torch.mul gives on the reference's tensors) and then widened.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double io_prod(float a, float b) { return (double)__fmul_rn(a, b); }
+__device__ __forceinline__ double io_prod(double a, double b) { return __dmul_rn(a, b); }
+
+// per-state scalar weight (w_obs, eps): the constant, the given value, or the square of the raw head output
+template <typename IO>
+__device__ __forceinline__ double load_state_weight(const KParams& P, const IO* p, long long sb, long long st,
+                                                    int b, int t, double dflt) {
+  if (p == nullptr) return dflt;
+  const IO v = __ldg(p + (long long)b * sb + (long long)t * st);
+  return (P.flags & FLAG_HEAD) ? io_prod(v, v) : (double)v;
+}
 
 // ---------------------------------------------------------------------------
 // SDF bilinear lookup (utils/sdf_utils.py:57-94)
@@ -116,6 +133,16 @@ __device__ __forceinline__ void load_qinv(const KParams& P, const KWeights<IO>& 
   constexpr int D = 2 * DOF;
   if (P.flags & FLAG_Q_FULL) {
     const IO* q = Wt.qc + (long long)b * Wt.qc_sb + (long long)i * Wt.qc_st;
+    if (P.flags & FLAG_HEAD) {          // 'q_full' head: Q^-1 = v v^T, v = d raw values (:274-278)
+      IO v[D];
+#pragma unroll
+      for (int a = 0; a < D; ++a) v[a] = __ldg(q + a);
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int c = 0; c < D; ++c) Q[a][c] = io_prod(v[a], v[c]);
+      return;
+    }
 #pragma unroll
     for (int a = 0; a < D; ++a)
 #pragma unroll
@@ -123,7 +150,25 @@ __device__ __forceinline__ void load_qinv(const KParams& P, const KWeights<IO>& 
     return;
   }
   double C[DOF][DOF];
-  if (Wt.qc != nullptr) {
+  if (Wt.qc != nullptr && (P.flags & FLAG_HEAD)) {
+    const IO* q = Wt.qc + (long long)b * Wt.qc_sb + (long long)i * Wt.qc_st;
+    if (P.flags & FLAG_HEAD_QC_VEC) {   // 'qc_full' head: Qc^-1 = v v^T, v = dof raw values (:269-273)
+      IO v[DOF];
+#pragma unroll
+      for (int a = 0; a < DOF; ++a) v[a] = __ldg(q + a);
+#pragma unroll
+      for (int a = 0; a < DOF; ++a)
+#pragma unroll
+        for (int c = 0; c < DOF; ++c) C[a][c] = io_prod(v[a], v[c]);
+    } else {                            // 'diag_identity' head: Qc^-1 = q^2 I (:256-262)
+      const IO v = __ldg(q);
+      const double qq = io_prod(v, v);
+#pragma unroll
+      for (int a = 0; a < DOF; ++a)
+#pragma unroll
+        for (int c = 0; c < DOF; ++c) C[a][c] = (a == c) ? qq : 0.0;
+    }
+  } else if (Wt.qc != nullptr) {
     const IO* q = Wt.qc + (long long)b * Wt.qc_sb + (long long)i * Wt.qc_st;
 #pragma unroll
     for (int a = 0; a < DOF; ++a)
@@ -356,8 +401,8 @@ __device__ __forceinline__ void assemble_node(const KParams& P, const KWeights<I
 
   // ---- obstacle factor (obstacle_factor.py:35-40; one sphere centred at (x, y), J_fk = [I2 0]) ----
   {
-    const double eps = (Wt.eps != nullptr) ? ldg_d(Wt.eps + (long long)b * Wt.e_sb + (long long)t * Wt.e_st) : P.eps_const;
-    const double w = (Wt.w != nullptr) ? ldg_d(Wt.w + (long long)b * Wt.w_sb + (long long)t * Wt.w_st) : P.w_const;
+    const double eps = load_state_weight<IO>(P, Wt.eps, Wt.e_sb, Wt.e_st, b, t, P.eps_const);
+    const double w = load_state_weight<IO>(P, Wt.w, Wt.w_sb, Wt.w_st, b, t, P.w_const);
     const double eps_tot = __dadd_rn(eps, P.r_sphere);
     const SdfSample s = sdf_bilinear<IO, false>(sdf_b, P.H, P.W, P.orig_x, P.orig_y, P.res, th[0], th[1], P.inv_res);
     const ObsTerm ob = hinge(s, eps_tot);
@@ -552,8 +597,8 @@ __device__ __forceinline__ void backward_node(const KParams& P, const KWeights<I
   }
   // ---- obstacle factor ----
   {
-    const double eps = (Wt.eps != nullptr) ? ldg_d(Wt.eps + (long long)b * Wt.e_sb + (long long)t * Wt.e_st) : P.eps_const;
-    const double w = (Wt.w != nullptr) ? ldg_d(Wt.w + (long long)b * Wt.w_sb + (long long)t * Wt.w_st) : P.w_const;
+    const double eps = load_state_weight<IO>(P, Wt.eps, Wt.e_sb, Wt.e_st, b, t, P.eps_const);
+    const double w = load_state_weight<IO>(P, Wt.w, Wt.w_sb, Wt.w_st, b, t, P.w_const);
     const double eps_tot = __dadd_rn(eps, P.r_sphere);
     const SdfCell c = sdf_cell<IO>(sdf_b, P.H, P.W, P.orig_x, P.orig_y, P.res, P.inv_res, th[0], th[1]);
     if (c.dist <= eps_tot) {

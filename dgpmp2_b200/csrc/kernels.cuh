@@ -517,7 +517,7 @@ factors_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
       for (int a = 0; a < D; ++a) gp_err[((size_t)b * (T - 1) + t) * D + a] = (IO)g[a];
     }
     if (obs_cost != nullptr || obs_H != nullptr) {
-      const double eps = (Wt.eps != nullptr) ? ldg_d(Wt.eps + (long long)b * Wt.e_sb + (long long)t * Wt.e_st) : P.eps_const;
+      const double eps = load_state_weight<IO>(P, Wt.eps, Wt.e_sb, Wt.e_st, b, t, P.eps_const);
       const SdfSample s = sdf_bilinear<IO>(sdf + (size_t)b * P.sdf_sb, P.H, P.W, P.orig_x, P.orig_y, P.res, thc[0], thc[1]);
       const ObsTerm ob = hinge(s, __dadd_rn(eps, P.r_sphere));
       if (obs_cost) obs_cost[i] = (IO)ob.c;
@@ -581,7 +581,7 @@ obstacle_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / T), t = (int)(i - (long long)b * T);
     const V2 pos = __ldg(reinterpret_cast<const V2*>(th + (size_t)i * D));
-    const double eps = (Wt.eps != nullptr) ? ldg_d(Wt.eps + (long long)b * Wt.e_sb + (long long)t * Wt.e_st) : P.eps_const;
+    const double eps = load_state_weight<IO>(P, Wt.eps, Wt.e_sb, Wt.e_st, b, t, P.eps_const);
     const SdfSample s = sdf_bilinear<IO, false>(sdf + (size_t)b * P.sdf_sb, P.H, P.W, P.orig_x, P.orig_y, P.res,
                                                 (double)pos.x, (double)pos.y, P.inv_res);
     const ObsTerm ob = hinge(s, __dadd_rn(eps, P.r_sphere));

@@ -8,7 +8,9 @@ learn_params=None, batch_size=1, use_cuda=False)``
       per-problem convergence in ONE persistent CUDA launch (dgpmp2_gn_solve_*), with identical
       per-problem semantics (independent problems, same stopping rule).
 The learned-covariance networks (reference learning/*, cuDNN model code) are outside this
-package; ``get_covariances`` (the mapping from network outputs to covariances, :247-290) is kept.
+package; ``get_covariances`` (the mapping from network outputs to covariances, :247-290) is kept, and
+the same mapping is available FUSED into the GN kernels: ``step_head(..., out)`` / a module installed
+with ``set_learn_module`` feed the network's raw output straight to the launch (DGPMP2_FLAG_HEAD).
 """
 import time
 
@@ -77,6 +79,9 @@ class DiffGPMP2Planner(nn.Module):
         pl._state = dict(start=startb, goal=goalb, qc=qc, w=w, eps=eps, static=True)
         needs_grad = torch.is_grad_enabled() and any(
             isinstance(t, torch.Tensor) and t.requires_grad for t in (th_initb, startb, goalb, sdfb))
+        if self.learn_module_fcn is not None:
+            # covariances re-predicted at every iterate (:128-147): batched step() loop through the fused head
+            return self._forward_timed(th_initb, startb, goalb, imb, sdfb, plan_time, start_t, torch.is_grad_enabled())
         if plan_time != float('inf') or needs_grad:
             # differentiable (unrolled, like the reference) or wall-clock-budgeted: batched step() loop
             return self._forward_timed(th_initb, startb, goalb, imb, sdfb, plan_time, start_t, needs_grad)
@@ -126,9 +131,39 @@ class DiffGPMP2Planner(nn.Module):
         return (th, None, [e[0] for e in epi], ef, epi, eepi, iters, [time.time() - start_t] * B)
 
     # ------------------------------------------------------------------ one iteration
+    def set_learn_module(self, module, dynamics_mode='diag_identity', learn_eps=False):
+        """Install a user-supplied learned module (the reference builds its own LearnModuleConv / LearnModuleFCN
+        from learn_params, :78-88; those networks are outside this package).  ``module(th_currb, imb, sdfb)`` must
+        return ``out`` (B,1,out_dim) laid out as ``get_covariances`` expects for ``dynamics_mode`` (:247-283).
+        ``step`` then runs the module and ONE fused launch that forms the covariances inside the GN kernel."""
+        from .. import _lib
+        _lib.head_block(dynamics_mode, self.dof)          # validates the mode
+        self.learn_module_fcn = module
+        self.dynamics_mode = dynamics_mode
+        self.learn_eps = bool(learn_eps)
+
+    def step_head(self, th_currb, startb, goalb, imb, sdfb, out, mode=None, learn_eps=None):
+        """One batched GN iteration from the learned module's raw output ``out`` (B,1,out_dim):
+        -> (dthetab, err_oldb, err_ext_oldb).  Equivalent to ``get_covariances(out, mode, learn_eps)`` followed by
+        ``plan_layer(...)`` (:196-206) without materialising the covariance tensors; differentiable w.r.t. ``out``."""
+        mode = mode or getattr(self, 'dynamics_mode', None) or 'diag_identity'
+        learn_eps = getattr(self, 'learn_eps', False) if learn_eps is None else learn_eps
+        return self.plan_layer.forward_head(th_currb, startb, goalb, imb, sdfb, out, mode, learn_eps)
+
     def step(self, th_currb, startb, goalb, imb, sdfb, conv_out=None, dtheta_currb=None, hiddenb=None):
         """One batched GN iteration -> (dthetab, hidden, err_oldb, err_ext_oldb, qc_inv, obscov_inv, eps)."""
         B = th_currb.shape[0]
+        if self.learn_module_fcn is not None:
+            out = self.learn_module_fcn(th_currb, imb, sdfb)
+            dthetab, err_oldb, err_ext_oldb = self.step_head(th_currb, startb, goalb, imb, sdfb, out)
+            with torch.no_grad():       # the covariances of the return tuple are reporting only (train_planner.py:310-311)
+                cov = self.get_covariances(out, self.dynamics_mode, self.learn_eps)
+                cov = list(cov) if isinstance(cov, tuple) else [cov]
+                if self.dynamics_mode == 'fix_dynamics':
+                    cov.insert(0, self.qc_inv_traj.to(out.device, out.dtype).unsqueeze(0).expand(B, -1, -1, -1))
+                if not self.learn_eps:
+                    cov.append(self.eps_traj.to(out.device, out.dtype).unsqueeze(0).expand(B, -1, -1, -1))
+            return dthetab, None, err_oldb, err_ext_oldb, cov[0], cov[1], cov[2]
         qc, w, eps = self.plan_layer.static_weights(B, th_currb)
         dthetab, err_oldb, err_ext_oldb = self.plan_layer(th_currb, startb, goalb, imb, sdfb, qc, w, eps)
         return dthetab, None, err_oldb, err_ext_oldb, qc, w, eps

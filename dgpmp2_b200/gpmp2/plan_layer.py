@@ -27,18 +27,22 @@ from .obstacle import ObstacleFactor
 class _GNStep(torch.autograd.Function):
     """dtheta, err, err_ext = GN step, differentiable w.r.t. th, start, goal, sdf, qc_inv, obscov_inv, eps.
     Forward: dgpmp2_gn_step_*; backward: dgpmp2_gn_step_backward_* (adjoint solve with the same block
-    cyclic reduction + factor VJPs).  err is not differentiable (the reference computes it under no_grad)."""
+    cyclic reduction + factor VJPs).  err is not differentiable (the reference computes it under no_grad).
+    With ``head`` (a dynamics_mode string) qc / w / eps are the RAW outputs of the learned module
+    (q (B,T-1,n), o (B,T), e (B,T); any may be None) and the kernels form the covariances themselves;
+    the backward kernel returns the gradients w.r.t. the covariances and the chain rule through the
+    products (q q^T, o^2, e^2) is applied here."""
 
     @staticmethod
-    def forward(ctx, layer, static, th, start, goal, sdf, qc, w, eps):
+    def forward(ctx, layer, static, head, th, start, goal, sdf, qc, w, eps):
         dt = work_dtype(th, sdf)
-        p = layer.cparams()
-        c = lambda t: to_cuda(t, dt)
+        p = layer.cparams(q_full=(head == 'q_full') if head is not None else None)
+        c = lambda t: to_cuda(t, dt) if t is not None else None
         thc, stc, goc, sdfc = c(th), c(start), c(goal), c(sdf)
-        kw = {} if static else dict(qc_inv=c(qc), w_obs=c(w), eps=c(eps))
+        kw = {} if static else dict(qc_inv=c(qc), w_obs=c(w), eps=c(eps), head=head)
         dth, err, err_ext, status = ops.gn_step(p, thc, stc, goc, sdfc, want_status=True, **kw)
         layer._check(status)
-        ctx.layer, ctx.static, ctx.dt = layer, static, dt
+        ctx.layer, ctx.static, ctx.head, ctx.dt = layer, static, head, dt
         ctx.meta = [(t.device, t.dtype, tuple(t.shape)) if isinstance(t, torch.Tensor) else None for t in (th, start, goal, sdf, qc, w, eps)]
         ctx.save_for_backward(thc, stc, goc, sdfc, dth, *([] if static else [kw['qc_inv'], kw['w_obs'], kw['eps']]))
         B = th.shape[0]
@@ -48,26 +52,39 @@ class _GNStep(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_dth, g_err, g_err_ext):
-        layer, static, dt = ctx.layer, ctx.static, ctx.dt
+        layer, static, head, dt = ctx.layer, ctx.static, ctx.head, ctx.dt
         saved = ctx.saved_tensors
         thc, stc, goc, sdfc, dth = saved[:5]
-        kw = {} if static else dict(qc_inv=saved[5], w_obs=saved[6], eps=saved[7])
-        need = ctx.needs_input_grad          # (layer, static, th, start, goal, sdf, qc, w, eps)
+        kw = {} if static else dict(qc_inv=saved[5], w_obs=saved[6], eps=saved[7], head=head)
+        need = ctx.needs_input_grad          # (layer, static, head, th, start, goal, sdf, qc, w, eps)
         B = thc.shape[0]
         gd = to_cuda(g_dth, dt) if g_dth is not None else torch.zeros_like(dth)
         ge = to_cuda(g_err_ext, dt).reshape(B) if g_err_ext is not None else None
-        outs = ops.gn_step_backward(layer.cparams(), thc, stc, goc, sdfc, dth, gd, ge,
-                                    need_th=need[2], need_start=need[3], need_goal=need[4], need_sdf=need[5],
-                                    need_qc=need[6] and not static, need_w=need[7] and not static,
-                                    need_eps=need[8] and not static, **kw)
+        p = layer.cparams(q_full=(head == 'q_full') if head is not None else None)
+        outs = ops.gn_step_backward(p, thc, stc, goc, sdfc, dth, gd, ge,
+                                    need_th=need[3], need_start=need[4], need_goal=need[5], need_sdf=need[6],
+                                    need_qc=need[7] and not static, need_w=need[8] and not static,
+                                    need_eps=need[9] and not static, **kw)
         g_th, g_start, g_goal, g_qc, g_w, g_eps, g_sdf = outs
+        if head is not None:
+            # chain rule through the head's products: Qc^-1 = q^2 I or v v^T, w = o^2, eps = e^2
+            q, o, e = saved[5], saved[6], saved[7]
+            if g_qc is not None:
+                if head == 'diag_identity':
+                    g_qc = 2.0 * q * torch.diagonal(g_qc, dim1=-2, dim2=-1).sum(-1, keepdim=True)
+                else:
+                    g_qc = torch.matmul(g_qc + g_qc.transpose(-1, -2), q.unsqueeze(-1)).squeeze(-1)
+            if g_w is not None:
+                g_w = 2.0 * o * g_w
+            if g_eps is not None:
+                g_eps = 2.0 * e * g_eps
 
         def fit(g, k):
             if g is None or ctx.meta[k] is None:
                 return None
             dev, dtype, shape = ctx.meta[k]
             return g.reshape(shape).to(device=dev, dtype=dtype)
-        return (None, None, fit(g_th, 0), fit(g_start, 1), fit(g_goal, 2), fit(g_sdf, 3), fit(g_qc, 4), fit(g_w, 5), fit(g_eps, 6))
+        return (None, None, None, fit(g_th, 0), fit(g_start, 1), fit(g_goal, 2), fit(g_sdf, 3), fit(g_qc, 4), fit(g_w, 5), fit(g_eps, 6))
 
 
 class PlanLayer(nn.Module):
@@ -169,9 +186,41 @@ class PlanLayer(nn.Module):
         self.obs_factor.set_inv_cov(obscov_inv_trajb)
         self.obs_factor.set_eps(eps_trajb)
         static = self._is_static(qc_inv_trajb, obscov_inv_trajb, eps_trajb)
-        self._state = dict(start=startb, goal=goalb, qc=qc_inv_trajb, w=obscov_inv_trajb, eps=eps_trajb, static=static)
+        self._state = dict(start=startb, goal=goalb, qc=qc_inv_trajb, w=obscov_inv_trajb, eps=eps_trajb, static=static, head=None)
         # expanded (broadcast) weight tensors are passed as they are; autograd sums their gradient
-        return _GNStep.apply(self, static, thb, startb, goalb, sdfb, qc_inv_trajb, obscov_inv_trajb, eps_trajb)
+        return _GNStep.apply(self, static, None, thb, startb, goalb, sdfb, qc_inv_trajb, obscov_inv_trajb, eps_trajb)
+
+    # ------------------------------------------------------------------ the GN step with the fused covariance head
+    def split_head(self, out, mode='diag_identity', learn_eps=False):
+        """The learned module's output ``out`` (B,1,out_dim) as the three raw slices the reference's
+        ``get_covariances`` multiplies out (diff_gpmp2_planner.py:247-283), as zero-copy views:
+        q (B,T-1,n) with n = 0 / 1 / dof / state_dim values per GP factor (None for 'fix_dynamics'),
+        o (B,T), e (B,T) or None."""
+        B = out.shape[0]
+        G, S = self.num_gp_factors, self.num_obs_factors * self.nlinks
+        n = _lib.head_block(mode, self.dof)
+        flat = out[:, 0] if out.dim() == 3 else out
+        need = G * n + S + (S if learn_eps else 0)
+        if flat.dim() != 2 or flat.shape[1] < need or (learn_eps and flat.shape[1] != need):
+            raise ValueError('head output must be (B,1,%d) for dynamics_mode %r, learn_eps=%s; got %s'
+                             % (need, mode, learn_eps, tuple(out.shape)))
+        q = flat[:, :G * n].reshape(B, G, n) if n else None
+        o = flat[:, G * n:G * n + S]
+        e = flat[:, G * n + S:G * n + 2 * S] if learn_eps else None
+        return q, o, e
+
+    def forward_head(self, thb, startb, goalb, imb, sdfb, out, mode=None, learn_eps=False):
+        """``forward`` fed with the learned module's raw output instead of the covariances: replaces
+        ``get_covariances`` + ``forward`` of the reference (diff_gpmp2_planner.py:183-206) by ONE launch --
+        the kernels square / outer-multiply the raw values while they assemble each state (DGPMP2_FLAG_HEAD),
+        so the (B,T-1,dof,dof), (B,T,1,1) covariance tensors never exist.  Differentiable w.r.t. ``out``.
+        Without ``learn_eps`` the constructor's epsilon_dist is used, as in the reference's ``step`` (:205)."""
+        mode = mode or self.dynamics_mode or 'diag_identity'
+        q, o, e = self.split_head(out, mode, learn_eps)
+        self.start_prior.set_mean(startb)
+        self.goal_prior.set_mean(goalb)
+        self._state = dict(start=startb, goal=goalb, qc=q, w=o, eps=e, static=False, head=mode)
+        return _GNStep.apply(self, False, mode, thb, startb, goalb, sdfb, q, o, e)
 
     def _check(self, status):
         self.last_status = status
@@ -183,15 +232,22 @@ class PlanLayer(nn.Module):
                                    '(first failing state %d)' % (b, int(status[b]) - 1))
 
     # ------------------------------------------------------------------ errors
+    def _installed(self, dt):
+        """(params, weight kwargs) of the covariances installed by the last forward() / forward_head()."""
+        s = self._state
+        head = s.get('head')
+        p = self.cparams(q_full=(head == 'q_full') if head is not None else None)
+        if s['static']:
+            return p, {}
+        c = lambda t: to_cuda(t.detach(), dt) if t is not None else None
+        return p, dict(qc_inv=c(s['qc']), w_obs=c(s['w']), eps=c(s['eps']), head=head)
+
     def _errors(self, thb, sdfb):
         if self._state is None:
             raise RuntimeError('PlanLayer: call forward() (or set the factor means / covariances) before error_batch')
         s = self._state
         dt = work_dtype(thb, sdfb)
-        p = self.cparams()
-        kw = {}
-        if not s['static']:
-            kw = dict(qc_inv=to_cuda(s['qc'], dt), w_obs=to_cuda(s['w'], dt), eps=to_cuda(s['eps'], dt))
+        p, kw = self._installed(dt)
         outs = ops.errors(p, to_cuda(thb, dt), to_cuda(s['start'], dt), to_cuda(s['goal'], dt), to_cuda(sdfb, dt), **kw)
         return [back(o, thb).to(thb.dtype) for o in outs]
 
@@ -226,7 +282,5 @@ class PlanLayer(nn.Module):
         D (B,T,d,d), U (B,T-1,d,d), r (B,T,d) -- what the reference holds as dense A^T K A + reg I, A^T K b."""
         s = self._state
         dt = work_dtype(thb, sdfb)
-        kw = {}
-        if not s['static']:
-            kw = dict(qc_inv=to_cuda(s['qc'], dt), w_obs=to_cuda(s['w'], dt), eps=to_cuda(s['eps'], dt))
-        return ops.band(self.cparams(), to_cuda(thb, dt), to_cuda(s['start'], dt), to_cuda(s['goal'], dt), to_cuda(sdfb, dt), **kw)
+        p, kw = self._installed(dt)
+        return ops.band(p, to_cuda(thb, dt), to_cuda(s['start'], dt), to_cuda(s['goal'], dt), to_cuda(sdfb, dt), **kw)

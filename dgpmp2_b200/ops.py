@@ -46,7 +46,19 @@ def _common(p: CParams, th, start, goal, sdf):
     return th, start, goal, sdf
 
 
-def _weights(p: CParams, dtype, qc_inv, w_obs, eps, B, T):
+def _weights(p: CParams, dtype, qc_inv, w_obs, eps, B, T, head=None):
+    """head: None -> qc_inv / w_obs / eps are covariances; a dynamics_mode string -> they are the RAW outputs
+    of the learned module (q_raw (B,T-1,n), o_raw (B,T), e_raw (B,T)) and the kernels form the covariances
+    themselves (fused get_covariances, DGPMP2_FLAG_HEAD)."""
+    if head is not None:
+        _lib.set_head_flags(p, head)
+        n = _lib.head_block(head, p.dof)
+        if (qc_inv is not None) != (n > 0):
+            raise ValueError("dynamics_mode %r %s a raw Qc output" % (head, 'needs' if n else 'does not take'))
+        if qc_inv is None and w_obs is None and eps is None:
+            raise ValueError('a covariance head needs at least one raw output')
+        w, keep = _lib.make_head_weights(_prep_w(qc_inv, dtype), _prep_w(w_obs, dtype), _prep_w(eps, dtype), B, T, n)
+        return ctypes.byref(w), keep + [w]
     if qc_inv is None and w_obs is None and eps is None:
         return None, []
     blk = 2 * p.dof if (p.flags & _lib.FLAG_Q_FULL) else p.dof
@@ -65,9 +77,10 @@ def _prep_w(t, dtype):
     return t if t.dtype == dtype else t.to(dtype)
 
 
-def gn_step(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, want_status=True, out=None):
+def gn_step(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, want_status=True, out=None, head=None):
     """One batched GN iteration. Returns dth (B,T,d), err (B,), err_ext (B,), status (B,) int32 or None.
-    `out`: optional preallocated contiguous CUDA tensor (B,T,d) of th's dtype that receives dth."""
+    `out`: optional preallocated contiguous CUDA tensor (B,T,d) of th's dtype that receives dth.
+    `head`: dynamics_mode string -> qc_inv / w_obs / eps are raw head outputs (see _weights)."""
     th, start, goal, sdf = _common(p, th, start, goal, sdf)
     B, T, d = th.shape
     if out is not None:
@@ -79,7 +92,7 @@ def gn_step(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None,
     err = torch.empty(B, dtype=th.dtype, device=th.device)
     err_ext = torch.empty_like(err)
     status = torch.empty(B, dtype=torch.int32, device=th.device) if want_status else None
-    wref, keep = _weights(p, th.dtype, qc_inv, w_obs, eps, B, T)
+    wref, keep = _weights(p, th.dtype, qc_inv, w_obs, eps, B, T, head)
     fn = getattr(load(), 'dgpmp2_gn_step_' + suffix(th.dtype))
     check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(sdf), wref, ptr(dth), ptr(err), ptr(err_ext),
              ptr(status), stream_ptr()))
@@ -88,7 +101,7 @@ def gn_step(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None,
 
 def gn_step_backward(p: CParams, th, start, goal, sdf, dth, g_dth, g_err_ext=None, qc_inv=None, w_obs=None, eps=None,
                      need_th=True, need_start=False, need_goal=False, need_qc=False, need_w=False, need_eps=False,
-                     need_sdf=False):
+                     need_sdf=False, head=None):
     """Backward of gn_step: returns (g_th, g_start, g_goal, g_qc, g_w, g_eps, g_sdf); entries not asked for are None.
     g_qc is dense (B,T-1,blk,blk), g_w / g_eps are (B,T), g_sdf has the layout of the (contiguous) sdf."""
     th, start, goal, sdf = _common(p, th, start, goal, sdf)
@@ -105,14 +118,15 @@ def gn_step_backward(p: CParams, th, start, goal, sdf, dth, g_dth, g_err_ext=Non
     g_w = torch.empty(B, T, dtype=dt, device=dev) if need_w else None
     g_eps = torch.empty(B, T, dtype=dt, device=dev) if need_eps else None
     g_sdf = torch.zeros_like(sdf) if need_sdf else None          # accumulated with atomics
-    wref, keep = _weights(p, dt, qc_inv, w_obs, eps, B, T)
+    wref, keep = _weights(p, dt, qc_inv, w_obs, eps, B, T, head)
     fn = getattr(load(), 'dgpmp2_gn_step_backward_' + suffix(dt))
     check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(sdf), wref, ptr(dth), ptr(g_dth), ptr(g_ee),
              ptr(g_th), ptr(g_start), ptr(g_goal), ptr(g_qc), ptr(g_w), ptr(g_eps), ptr(g_sdf), stream_ptr()))
     return g_th, g_start, g_goal, g_qc, g_w, g_eps, g_sdf
 
 
-def gn_solve(p: CParams, th, start, goal, sdf, max_iters: int, tol_delta: float, qc_inv=None, w_obs=None, eps=None):
+def gn_solve(p: CParams, th, start, goal, sdf, max_iters: int, tol_delta: float, qc_inv=None, w_obs=None, eps=None,
+             head=None):
     """Persistent solve to convergence. Returns th_final, iters, err_per_iter (B,max_iters; NaN beyond iters),
     err_ext_per_iter, err_final, err_ext_final, status."""
     th, start, goal, sdf = _common(p, th, start, goal, sdf)
@@ -125,19 +139,19 @@ def gn_solve(p: CParams, th, start, goal, sdf, max_iters: int, tol_delta: float,
     ef = torch.empty(B, dtype=dt, device=dev)
     eef = torch.empty(B, dtype=dt, device=dev)
     status = torch.empty(B, dtype=torch.int32, device=dev)
-    wref, keep = _weights(p, dt, qc_inv, w_obs, eps, B, T)
+    wref, keep = _weights(p, dt, qc_inv, w_obs, eps, B, T, head)
     fn = getattr(load(), 'dgpmp2_gn_solve_' + suffix(dt))
     check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(sdf), wref, int(max_iters), float(tol_delta),
              ptr(th_final), ptr(iters), ptr(epi), ptr(eepi), ptr(ef), ptr(eef), ptr(status), stream_ptr()))
     return th_final, iters, epi, eepi, ef, eef, status
 
 
-def errors(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None):
+def errors(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, head=None):
     """Factor sweep. Returns err, err_ext, err_sg, err_gp, err_obs, each (B,)."""
     th, start, goal, sdf = _common(p, th, start, goal, sdf)
     B, T, d = th.shape
     outs = [torch.empty(B, dtype=th.dtype, device=th.device) for _ in range(5)]
-    wref, keep = _weights(p, th.dtype, qc_inv, w_obs, eps, B, T)
+    wref, keep = _weights(p, th.dtype, qc_inv, w_obs, eps, B, T, head)
     fn = getattr(load(), 'dgpmp2_errors_' + suffix(th.dtype))
     check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(sdf), wref, *[ptr(o) for o in outs], stream_ptr()))
     return tuple(outs)
@@ -199,14 +213,14 @@ def sdf_from_occupancy(im, padlen: int = 1, res: float = 1.0, thresh: float = 0.
     return out
 
 
-def band(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None):
+def band(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, head=None):
     """Information band in float64: D (B,T,d,d), U (B,T-1,d,d), r (B,T,d)."""
     th, start, goal, sdf = _common(p, th, start, goal, sdf)
     B, T, d = th.shape
     D = torch.empty(B, T, d, d, dtype=torch.float64, device=th.device)
     U = torch.empty(B, T - 1, d, d, dtype=torch.float64, device=th.device)
     r = torch.empty(B, T, d, dtype=torch.float64, device=th.device)
-    wref, keep = _weights(p, th.dtype, qc_inv, w_obs, eps, B, T)
+    wref, keep = _weights(p, th.dtype, qc_inv, w_obs, eps, B, T, head)
     fn = getattr(load(), 'dgpmp2_band_' + suffix(th.dtype))
     check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(sdf), wref, ptr(D), ptr(U), ptr(r), stream_ptr()))
     return D, U, r

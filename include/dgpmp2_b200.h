@@ -41,6 +41,17 @@ extern "C" {
 #define DGPMP2_FLAG_NONHOLONOMIC 1  /* planner_params['non_holonomic'];  needs dof == 3 */
 #define DGPMP2_FLAG_VEL_LIMITS 2    /* planner_params['use_vel_limits']; needs dof == 2 */
 #define DGPMP2_FLAG_Q_FULL 4        /* learn_params dynamics_mode == 'q_full': weights.qc_inv holds full d x d Q^-1 */
+/* Fused learned-covariance head (replaces DiffGPMP2Planner.get_covariances, diff_gpmp2_planner.py:247-283):
+ * the non-NULL pointers of dgpmp2_weights hold the RAW outputs of the learned module and the kernels form
+ * the covariances themselves, with the reference's rounding (products taken in the I/O element type):
+ *   w_obs = o*o (:275), eps = e*e (:279) and, per GP factor,
+ *   qc_inv = q*q * I_dof from ONE value        ('diag_identity', :256-262; DGPMP2_FLAG_HEAD alone),
+ *   qc_inv = v v^T from dof values             ('qc_full',  :269-273; with DGPMP2_FLAG_HEAD_QC_VEC),
+ *   Q^-1   = v v^T from d = 2*dof values       ('q_full',   :274-278; with DGPMP2_FLAG_Q_FULL).
+ * qc_stride_t is then the distance between the factors' raw values (1, dof or d for a packed vector).
+ * The backward entry points still return the gradients w.r.t. the covariances (g_qc, g_w, g_eps). */
+#define DGPMP2_FLAG_HEAD 8
+#define DGPMP2_FLAG_HEAD_QC_VEC 16
 
 /*
  * Constructor-time constants of the planner (reference plan_layer.py:14-85,
@@ -80,6 +91,7 @@ typedef struct dgpmp2_params {
  *   qc_inv : blocks of dof*dof (or d*d with DGPMP2_FLAG_Q_FULL), one per GP factor i in [0,T-1)
  *   w_obs  : one scalar per state (obscov_inv, nlinks == 1)
  *   eps    : one scalar per state
+ * With DGPMP2_FLAG_HEAD the same pointers hold the raw head outputs instead (see the flag).
  */
 typedef struct dgpmp2_weights {
   const void* qc_inv; int64_t qc_stride_b, qc_stride_t;

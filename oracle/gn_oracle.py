@@ -389,6 +389,35 @@ def fixed_covariances(p: GNParams, B: int):
     return gp_inv_cov(qc, p.dt), w
 
 
+def covariances_from_head(out, p: GNParams, mode: str = 'diag_identity', learn_eps: bool = False):
+    """``DiffGPMP2Planner.get_covariances`` (diff_gpmp2_planner.py:247-283): the learned module's output
+    ``out`` (B,1,out_dim) = [q | o | e] -> (qc_inv or None, obscov_inv (B,T,1,1), eps (B,T,1,1) or None).
+
+    'fix_dynamics': no q part (:250-253); 'diag_identity': one value per GP factor, Qc^-1 = q*q * I_dof
+    (:254-260); 'qc_full': dof values, Qc^-1 = v v^T (:267-271); 'q_full': state_dim values, Q^-1 = v v^T
+    (:272-276); obscov_inv = o*o (:278); eps = e*e (:280-282).  nlinks = 1.  Pinned against the live
+    reference by tests/golden/head_*.npz (oracle/make_golden_head.py).
+    """
+    out = _f64(out)
+    B = out.shape[0]
+    G, S, d = p.T - 1, p.T, 2 * p.dof
+    n = {'fix_dynamics': 0, 'diag_identity': 1, 'qc_full': p.dof, 'q_full': d}[mode]
+    row = out[:, 0, :]
+    qc = None
+    if n:
+        v = row[:, :G * n].reshape(B, G, n, 1)
+        qc = v * v.transpose(2, 3)
+        if mode == 'diag_identity':
+            qc = qc * torch.eye(p.dof, dtype=F64)
+    o = row[:, G * n:G * n + S].reshape(B, S, 1, 1)
+    w = o * o
+    eps = None
+    if learn_eps:
+        e = row[:, G * n + S:].reshape(B, S, 1, 1)
+        eps = e * e
+    return qc, w, eps
+
+
 def gn_step(th, start, goal, sdf, qc_inv, w_obs, eps, p: GNParams, q_full: bool = False):
     """``PlanLayer.forward`` (plan_layer.py:87-99) -> (dtheta (B,T,d), err (B,1,1), err_ext (B,1,1)).
 

@@ -56,3 +56,20 @@ def rel_err(a, b):
     a = torch.as_tensor(a).double().reshape(a.shape[0], -1)
     b = torch.as_tensor(b).double().reshape(b.shape[0], -1)
     return (torch.linalg.norm(a - b, dim=1) / torch.linalg.norm(b, dim=1).clamp_min(1e-300)).max().item()
+
+
+def head_cases():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, 'head_*.npz')))
+
+
+def head_oracle_weights(g, p):
+    """Covariances of a head_* golden case via the oracle's restatement of get_covariances, with the
+    static values where the mode / learn_eps leaves them constant -> (qc, w, eps, q_full)."""
+    mode, learn_eps = str(g['mode']), bool(g['learn_eps'])
+    B, T = g['th'].shape[0], int(g['T'])
+    qc, w, eps = gn_oracle.covariances_from_head(t64(g['out']), p, mode, learn_eps)
+    if qc is None:
+        qc = torch.tensor(p.Q_c_inv, dtype=torch.float64).expand(B, T - 1, p.dof, p.dof)
+    if eps is None:
+        eps = torch.full((B, T, 1, 1), p.epsilon_dist, dtype=torch.float64)
+    return qc, w, eps, mode == 'q_full'
