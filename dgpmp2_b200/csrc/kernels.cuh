@@ -619,7 +619,8 @@ sdf_lookup_kernel(const IO* __restrict__ sdf, int B, int H, int W, long long sdf
 // datasets/utils.py:4-18), i.e. two scipy.ndimage.distance_transform_edt calls per map.
 // One CTA per image.  Pass 1: per column, distance to the nearest background pixel of that column
 // (both polarities at once).  Pass 2: per pixel, exact minimum over the row of dx^2 + g^2 in integer
-// arithmetic, then sqrt in double: bit-identical to the exact EDT.  scipy's behaviour for an image
+// arithmetic (one polarity per pixel, scanned outwards with an exact cut-off), then sqrt in double:
+// bit-identical to the exact EDT.  scipy's behaviour for an image
 // WITHOUT any background pixel (distance to a virtual pixel at row -1, column 0) is reproduced.
 // ---------------------------------------------------------------------------
 template <typename IO>
@@ -660,19 +661,25 @@ sdf_from_occupancy_kernel(const IO* __restrict__ im, int H, int W, int pad, doub
   IO* dst = out + (size_t)blockIdx.x * Hp * Wp;
   for (int i = threadIdx.x; i < Hp * Wp; i += blockDim.x) {
     const int y = i / Wp, x = i - y * Wp;
-    long long b0 = -1, b1 = -1;
-    const unsigned short* r0 = g0 + (size_t)y * Wp;
-    const unsigned short* r1 = g1 + (size_t)y * Wp;
-    for (int xp = 0; xp < Wp; ++xp) {
-      const long long dx2 = (long long)(x - xp) * (x - xp);
-      const unsigned short a0 = r0[xp], a1 = r1[xp];
-      if (a0 != INF) { const long long c = dx2 + (long long)a0 * a0; b0 = (b0 < 0 || c < b0) ? c : b0; }
-      if (a1 != INF) { const long long c = dx2 + (long long)a1 * a1; b1 = (b1 < 0 || c < b1) ? c : b1; }
+    // A pixel is background of one of the two transforms (distance 0 there), so only ONE row scan is needed:
+    // free pixels look for the nearest obstacle (g0), obstacle pixels for the nearest free pixel (g1).
+    const bool is_free = g1[(size_t)y * Wp + x] == 0;
+    const unsigned short* r = (is_free ? g0 : g1) + (size_t)y * Wp;
+    // exact minimum over the row of dx^2 + g^2, scanned outwards from x: columns with dx^2 >= the best value so
+    // far cannot improve it.  32-bit integers suffice: Hp * Wp <= 58 112 by the shared-memory limit, so Hp^2 + Wp^2 < 2^32.
+    const unsigned a_c = r[x];
+    unsigned best = (a_c == INF) ? 0xffffffffu : a_c * a_c;
+    for (int k = 1; k < Wp; ++k) {
+      const unsigned k2 = (unsigned)k * (unsigned)k;
+      if (k2 >= best) break;
+      if (x - k >= 0) { const unsigned a = r[x - k]; if (a != INF) best = min(best, k2 + a * a); }
+      if (x + k < Wp) { const unsigned a = r[x + k]; if (a != INF) best = min(best, k2 + a * a); }
     }
     // no background pixel at all: scipy (1.18) measures from a virtual pixel at row -1, column 0
     const double quirk = sqrt((double)((long long)(y + 1) * (y + 1) + (long long)x * x));
-    const double d_free = has_obst ? sqrt((double)b0) : quirk;      // EDT(im): free pixels -> nearest obstacle
-    const double d_obst = has_free ? sqrt((double)b1) : quirk;      // EDT(1 - im): obstacle pixels -> nearest free
+    const double d_scan = sqrt((double)best);
+    const double d_free = is_free ? (has_obst ? d_scan : quirk) : 0.0;     // EDT(im): free pixels -> nearest obstacle
+    const double d_obst = is_free ? 0.0 : (has_free ? d_scan : quirk);     // EDT(1 - im): obstacle pixels -> nearest free
     dst[i] = (IO)((d_free - d_obst) * res);
   }
 }
