@@ -23,6 +23,7 @@ int cuda_fail(cudaError_t e) {
 }
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_); } while (0)
 
+constexpr int kPdlDefault = 2;       // DGPMP2_PDL: 1 = plain launches, 2 = programmatic dependent launch of gn_step (default)
 constexpr int kSmemLimit = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
 
 int check_params(const dgpmp2_params* p, const dgpmp2_weights* w) {
@@ -200,6 +201,22 @@ int launch_step(const KParams& k, const KWeights<IO>& kw, const IO* th, const IO
   auto kern = gn_step_kernel<DOF, IO>;
   rc = allow_smem(kern, s.smem);
   if (rc != DGPMP2_OK) return rc;
+  if (env_int("DGPMP2_PDL", kPdlDefault) == 2) {
+    // programmatic dependent launch: the launch latency of step n + 1 hides behind step n (the kernel waits at
+    // griddepcontrol.wait before it touches global memory, so stream order is preserved for every access)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)s.grid);
+    cfg.blockDim = dim3((unsigned)s.threads);
+    cfg.dynamicSmemBytes = (size_t)s.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, k, kw, th, start, goal, sdf, dth, err, err_ext, status, s.np));
+    return DGPMP2_OK;
+  }
   kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, s.np);
   CUDA_TRY(cudaGetLastError());
   return DGPMP2_OK;

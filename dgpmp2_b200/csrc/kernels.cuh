@@ -179,6 +179,11 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
   S.carve(smem_raw, NP, T, 0);
   const int b0 = blockIdx.x * NP;
   const int np = min(NP, P.B - b0);
+  // Programmatic dependent launch (c_abi.cu: launch_step): let the next launch of the stream be scheduled onto the
+  // SMs as soon as this grid's CTAs leave them, and wait here -- before the first global access -- until the
+  // previous grid of the stream has completed and its writes are visible.  Both are no-ops for a plain launch.
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   DGPMP2_STAMP(0);
 
   cta_prologue<D, IO>(P, S, T, NP, np, th + (size_t)b0 * T * D, false);
