@@ -23,7 +23,7 @@ int cuda_fail(cudaError_t e) {
 }
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_); } while (0)
 
-constexpr int kPdlDefault = 2;       // DGPMP2_PDL: 1 = plain launches, 2 = programmatic dependent launch of gn_step (default)
+constexpr int kPdlDefault = 1;       // DGPMP2_PDL: 1 = plain launches (default), 2 = programmatic dependent launch of gn_step
 constexpr int kSmemLimit = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
 
 int check_params(const dgpmp2_params* p, const dgpmp2_weights* w) {

@@ -1,6 +1,6 @@
-"""-m gpu: gn_step is launched with programmatic dependent launch (DGPMP2_PDL=2, the default; c_abi.cu launch_step):
-the next step may be scheduled before the previous grid has drained, but every global access of the kernel comes
-after griddepcontrol.wait.  Dependent chains of launches (th <- th + dth with a plain torch kernel in between, and
+"""-m gpu: gn_step can be launched with programmatic dependent launch (DGPMP2_PDL=2; c_abi.cu launch_step; opt-in,
+see DESIGN.md 4.1): the next step may be scheduled before the previous grid has drained, but every global access
+of the kernel comes after griddepcontrol.wait.  Dependent chains of launches (th <- th + dth with a plain torch kernel in between, and
 launches that overwrite one output buffer) must therefore give the bits of plain launches (DGPMP2_PDL=1), eagerly
 and when the chain is captured in a CUDA graph (how bench.py times the step)."""
 import os
