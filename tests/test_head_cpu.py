@@ -204,3 +204,37 @@ def test_planner_step_with_learn_module_host_logic(monkeypatch):
     assert res[6] == [2] * B
     res[0].sum().backward()
     assert scale.grad is not None and float(scale.grad.abs()) > 0
+
+
+def test_header_constants_match_the_python_binding_and_head_flags_are_checked_without_a_gpu():
+    """include/dgpmp2_b200.h is the contract: its #defines equal the constants the ctypes binding uses, and the
+    C ABI rejects inconsistent head flags before anything is launched (runs on the CPU box)."""
+    import ctypes
+    import os
+    import re
+    from dgpmp2_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, 'include', 'dgpmp2_b200.h')).read()
+    defs = {k: int(v.strip('()')) for k, v in re.findall(r'#define\s+(DGPMP2_[A-Z_0-9]+)\s+(\(?-?\d+\)?)', src)}
+    assert defs['DGPMP2_FLAG_NONHOLONOMIC'] == _lib.FLAG_NONHOLONOMIC and defs['DGPMP2_FLAG_VEL_LIMITS'] == _lib.FLAG_VEL_LIMITS
+    assert defs['DGPMP2_FLAG_Q_FULL'] == _lib.FLAG_Q_FULL
+    assert defs['DGPMP2_FLAG_HEAD'] == _lib.FLAG_HEAD and defs['DGPMP2_FLAG_HEAD_QC_VEC'] == _lib.FLAG_HEAD_QC_VEC
+    assert defs['DGPMP2_OK'] == _lib.OK and defs['DGPMP2_ERR_ARG'] == _lib.ERR_ARG
+    assert defs['DGPMP2_ERR_UNSUPPORTED'] == _lib.ERR_UNSUPPORTED and defs['DGPMP2_ERR_CUDA'] == _lib.ERR_CUDA
+    flags = [v for k, v in defs.items() if k.startswith('DGPMP2_FLAG_')]
+    assert len(set(flags)) == len(flags) and all(f & (f - 1) == 0 for f in flags)      # distinct single bits
+
+    lib = _lib.load()
+    p = _lib.make_params(4, 16, 2, 16, 16, (-5, 5), (-5, 5), 10.0, 0.4, 0.01, 0.01, 0.1, torch.eye(2), 0.01, 0.4)
+    null = ctypes.c_void_p(0)
+    call = lambda w: lib.dgpmp2_gn_step_f32(ctypes.byref(p), null, null, null, null, w, null, null, null, null, null)
+    w = _lib.CWeights()
+    p.flags = _lib.FLAG_HEAD
+    assert call(None) == _lib.ERR_ARG                       # a head without outputs
+    p.flags = _lib.FLAG_HEAD_QC_VEC
+    assert call(ctypes.byref(w)) == _lib.ERR_ARG            # QC_VEC qualifies HEAD
+    p.flags = 32
+    assert call(ctypes.byref(w)) == _lib.ERR_ARG            # unknown flag bit
+    p.flags = _lib.FLAG_HEAD | _lib.FLAG_HEAD_QC_VEC
+    p.B = 0
+    assert call(ctypes.byref(w)) == _lib.OK                 # consistent flags, empty batch: accepted, nothing launched
