@@ -214,7 +214,11 @@ class PlanLayer(nn.Module):
         ``get_covariances`` + ``forward`` of the reference (diff_gpmp2_planner.py:183-206) by ONE launch --
         the kernels square / outer-multiply the raw values while they assemble each state (DGPMP2_FLAG_HEAD),
         so the (B,T-1,dof,dof), (B,T,1,1) covariance tensors never exist.  Differentiable w.r.t. ``out``.
-        Without ``learn_eps`` the constructor's epsilon_dist is used, as in the reference's ``step`` (:205)."""
+        Without ``learn_eps`` the constructor's epsilon_dist is used, as in the reference's ``step`` (:205).
+        Statefulness: the start / goal means are installed on the prior factors and ``error_batch`` /
+        ``error_ext_batch`` / ``information_band`` evaluate with this call's covariances, as after ``forward``; the
+        covariance attributes of ``gp_prior`` / ``obs_factor`` are NOT rewritten (those tensors are never formed) --
+        call ``get_covariances`` + ``forward`` when stand-alone factor objects must carry them."""
         mode = mode or self.dynamics_mode or 'diag_identity'
         q, o, e = self.split_head(out, mode, learn_eps)
         self.start_prior.set_mean(startb)
