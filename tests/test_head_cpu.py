@@ -112,7 +112,9 @@ def _fake_ops(monkeypatch, T, x_lims, y_lims):
     from dgpmp2_b200.gpmp2 import plan_layer as pl_mod
 
     def cov(p, qc_inv, w_obs, eps, head, B):
-        op = oracle_params(T, x_lims, y_lims)
+        # the constructor-time constants travel in the params struct (1/sigma^2, Qc^-1, eps), as for the kernels
+        op = oracle_params(T, x_lims, y_lims, cost_sigma=p.w_obs_fix ** -0.5,
+                           Q_c_inv=[[p.qc_inv_fix[0], p.qc_inv_fix[1]], [p.qc_inv_fix[2], p.qc_inv_fix[3]]], epsilon_dist=p.eps)
         if head is not None:
             n = _lib.head_block(head, 2)
             assert (qc_inv is None) == (n == 0)
@@ -127,9 +129,11 @@ def _fake_ops(monkeypatch, T, x_lims, y_lims):
         else:
             qc, w, e = qc_inv, w_obs, eps
         if qc is None:
-            qc = torch.tensor(op.Q_c_inv, dtype=torch.float64).expand(B, T - 1, 2, 2)
+            qc = torch.tensor([p.qc_inv[i] for i in range(4)], dtype=torch.float64).reshape(2, 2).expand(B, T - 1, 2, 2)
+        if w is None:
+            w = torch.full((B, T, 1, 1), p.w_obs, dtype=torch.float64)
         if e is None:
-            e = torch.full((B, T, 1, 1), op.epsilon_dist, dtype=torch.float64)
+            e = torch.full((B, T, 1, 1), p.eps, dtype=torch.float64)
         return op, qc, w, e
 
     def gn_step(p, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, want_status=True, out=None, head=None):
@@ -162,6 +166,15 @@ def _fake_ops(monkeypatch, T, x_lims, y_lims):
         z = torch.zeros(B, dtype=torch.float64)
         return err.reshape(B), err_ext.reshape(B), z, z, z
 
+    def gn_solve(p, th, start, goal, sdf, max_iters, tol_delta, qc_inv=None, w_obs=None, eps=None, head=None):
+        B = th.shape[0]
+        op, qc, w, e = cov(p, qc_inv, w_obs, eps, head, B)
+        th_f, e0, ef, epi, eepi, iters = gn_oracle.gn_solve(th, start, goal, sdf, qc, w, e, op, max_iters, tol_delta)
+        pad = lambda rows: torch.tensor([r + [float('nan')] * (max_iters - len(r)) for r in rows], dtype=torch.float64)
+        return (th_f, torch.tensor(iters, dtype=torch.int32), pad(epi), pad(eepi), torch.tensor(ef, dtype=torch.float64),
+                torch.tensor(ef, dtype=torch.float64), torch.zeros(B, dtype=torch.int32))
+
+    monkeypatch.setattr(ops, 'gn_solve', gn_solve)
     monkeypatch.setattr(ops, 'gn_step', gn_step)
     monkeypatch.setattr(ops, 'gn_step_backward', gn_step_backward)
     monkeypatch.setattr(ops, 'errors', errors)
@@ -238,3 +251,25 @@ def test_header_constants_match_the_python_binding_and_head_flags_are_checked_wi
     p.flags = _lib.FLAG_HEAD | _lib.FLAG_HEAD_QC_VEC
     p.B = 0
     assert call(ctypes.byref(w)) == _lib.OK                 # consistent flags, empty batch: accepted, nothing launched
+
+
+def test_learning_example_runs_with_oracle_backed_ops(monkeypatch):
+    """examples/learn_covariances_headless.py (expert labels by the persistent solve, K unrolled differentiable steps
+    through the fused head, one flat gradient all-reduce per optimiser step): its host logic end to end, CPU tensors,
+    the CUDA entry points replaced by the oracle."""
+    import importlib.util
+    import os
+    from dgpmp2_b200 import _dev
+    from dgpmp2_b200.gpmp2 import diff_gpmp2_planner as pm
+    T = 8
+    _fake_ops(monkeypatch, T, (-5.0, 5.0), (-5.0, 5.0))
+    monkeypatch.setattr(pm, 'to_cuda', lambda t, dt=None: None if t is None else t.detach().to(dt))
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'examples', 'learn_covariances_headless.py')
+    spec = importlib.util.spec_from_file_location('learn_example', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    losses, head = mod.main(['--batch', '3', '--states', str(T), '--unroll', '2', '--iters', '4', '--device', 'cpu', '--f64'])
+    assert len(losses) == 4 and all(l == l and l < float('inf') for l in losses)
+    assert losses[-1] < losses[0]                              # the imitation loss goes down
+    assert float(head.lin.bias.grad.abs().max()) > 0 and float(head.lin.weight.grad.abs().max()) > 0
+    assert _dev is not None
