@@ -12,7 +12,8 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libdgpmp2_b200.so')
+# DGPMP2_LIB: load another build of the same ABI instead (A/B timing of experimental builds, scratch/*.sh)
+LIB_PATH = os.environ.get('DGPMP2_LIB') or os.path.join(_HERE, 'lib', 'libdgpmp2_b200.so')
 
 FLAG_NONHOLONOMIC = 1
 FLAG_VEL_LIMITS = 2

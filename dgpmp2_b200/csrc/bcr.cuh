@@ -614,10 +614,12 @@ __device__ __forceinline__ void bcr_tail(double* __restrict__ nodes, int T, int 
 // the sparse deep levels of several problems share warps.  A level with at least plan.wide_min items
 // in the CTA runs one lane per item, the others kLPN lanes per item.  Elimination stops after
 // plan.nl levels; the remaining chain of plan.tail_nc nodes is solved sequentially (bcr_tail).
+// level1_eliminated (uniform): the records of the level-1 nodes already hold L, E, F, g (skip that phase).
 // On exit every record's [oR, oR+D) holds x_t.  fail[p] (shared, pre-zeroed) receives t+1 of a node
 // of problem p whose pivot was not positive.  Must be called by ALL threads of the CTA (barriers).
 template <int D>
-__device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const BcrPlan& plan, int T, int np, int* fail) {
+__device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const BcrPlan& plan, int T, int np, int* fail,
+                                          bool level1_eliminated = false) {
   const int nl = plan.nl, wide_min = plan.wide_min;
 
   // ------------------------------ forward elimination ------------------------------
@@ -627,10 +629,12 @@ __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const BcrP
     const BcrLevelPlan& lv = plan.lv[l - 1];
     const LevelDiv dv_e = {lv.ne, lv.e_sh, lv.e_inv}, dv_k = {lv.nk, lv.k_sh, lv.k_inv};
     const bool wide = np * lv.ne >= wide_min;    // uniform
-    DGPMP2_REP(1, l)
-    if (wide) bcr_elim_level<D, 1>(nodes, T, np, s, dv_e, off_l, fail);
-    else      bcr_elim_level<D, kLPN>(nodes, T, np, s, dv_e, off_l, fail);
-    __syncthreads();
+    if (!(level1_eliminated && l == 1)) {   // (the assembly already wrote the level-1 nodes in eliminated form: kernels.cuh fuse1)
+      DGPMP2_REP(1, l)
+      if (wide) bcr_elim_level<D, 1>(nodes, T, np, s, dv_e, off_l, fail);
+      else      bcr_elim_level<D, kLPN>(nodes, T, np, s, dv_e, off_l, fail);
+      __syncthreads();
+    }
     DGPMP2_BCR_STAMP(8 + 2 * l);
     DGPMP2_REP(2, l)
     if (wide) bcr_kept_level<D, 1>(nodes, T, np, s, dv_k, off_l);

@@ -54,11 +54,17 @@ struct StepSmem {
 
 // Assemble the CTA's np * T nodes (one thread per node record, records enumerated problem-major
 // in slot order) from the staged trajectory.
+//
+// fuse1 (experimental, compiled only with -DDGPMP2_EXPERIMENTAL_FUSE1; uniform; requires P.static_gp and at least
+// one elimination level): the thread of a level-1 node (odd state j) eliminates it straight from its registers
+// -- L_j, F_j = L^-1 U_j, g_j = L^-1 r_j and E_j = L^-1 U_{j-1}^T with U_{j-1} = -Phi^T Q^-1, a host-known constant in
+// the static-GP case -- and writes the record once in its eliminated form; bcr_solve then skips the level-1
+// elimination phase and its barrier.  Same arithmetic on the same doubles as bcr_elim_level: bit-identical results.
 template <int DOF, typename IO>
 __device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO>& Wt, const StepSmem<2 * DOF, IO>& S,
                                              int b0, int np,
                                              const IO* __restrict__ start, const IO* __restrict__ goal,
-                                             const IO* __restrict__ sdf) {
+                                             const IO* __restrict__ sdf, bool fuse1 = false) {
   constexpr int D = 2 * DOF;
   using N = Node<D>;
   const int T = P.T;
@@ -79,6 +85,38 @@ __device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO
     assemble_node<DOF, IO>(P, Wt, b, t, thp, thc, thn, start + (size_t)b * D, goal + (size_t)b * D,
                            sdf + (size_t)b * P.sdf_sb, o);
     double* nd = S.nodes + (size_t)p * N::problem_stride(T) + (size_t)slot * N::kStride;
+#ifdef DGPMP2_EXPERIMENTAL_FUSE1
+    if (fuse1 && slot < P.plan.lv[0].ne) {          // level-1 node: the slots [0, ne) of level order
+      constexpr int DS = N::DS;
+      double L[DS];
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int c = 0; c <= a; ++c) L[tri(a, c)] = o.Dm[a][c];
+      if (!chol_packed<D>(L)) atomicMax(&S.fail[p], t + 1);
+#pragma unroll
+      for (int k = 0; k < DS; k += 2) sts2(nd + N::oD + k, L[k], (k + 1 < DS) ? L[k + 1] : 0.0);
+      double v[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) {                 // F_j = L^-1 U_j, column-major (U_j = 0 for the last state)
+#pragma unroll
+        for (int a = 0; a < D; ++a) v[a] = o.Um[a][c];
+        fwd_solve<D>(L, v);
+        st_vec<D>(nd + N::oU + c * D, v);
+      }
+      fwd_solve<D>(L, o.r);
+      st_vec<D>(nd + N::oR, o.r);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {                 // E_j = L^-1 U_{j-1}^T: column c = row c of U_{j-1} = -Phi^T Q^-1
+#pragma unroll
+        for (int a = 0; a < D; ++a) v[a] = -P.PQs[c * D + a];
+        fwd_solve<D>(L, v);
+        st_vec<D>(nd + N::oE + c * D, v);
+      }
+      sts2(nd + N::oX, o.err, o.err_ext);
+      continue;
+    }
+#endif
 #pragma unroll
     for (int a = 0; a < D; ++a) {
       st_vec<D>(nd + N::oD + a * D, o.Dm[a]);
@@ -190,11 +228,16 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
   __syncthreads();
   DGPMP2_STAMP(1);
 
-  assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf);
+#ifdef DGPMP2_EXPERIMENTAL_FUSE1
+  const bool fuse1 = P.static_gp != 0 && P.plan.nl >= 1;      // uniform
+#else
+  constexpr bool fuse1 = false;
+#endif
+  assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf, fuse1);
   __syncthreads();
   DGPMP2_STAMP(2);
 
-  bcr_solve<D>(S.nodes, P.plan, T, np, S.fail);   // ends with a barrier
+  bcr_solve<D>(S.nodes, P.plan, T, np, S.fail, fuse1);   // ends with a barrier
   DGPMP2_STAMP(3);
 
   {  // dth, natural order -> coalesced stores
