@@ -60,6 +60,7 @@ PROTOTYPES = {
     'dgpmp2_last_cuda_error': [],
     'dgpmp2_gn_step_f32': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp],
     'dgpmp2_gn_step_f64': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp],
+    'dgpmp2_gn_step_diag_f32': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp, _vp],
     'dgpmp2_gn_step_backward_f32': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     'dgpmp2_gn_step_backward_f64': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     'dgpmp2_gn_solve_f32': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],

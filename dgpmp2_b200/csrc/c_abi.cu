@@ -10,6 +10,7 @@
 
 #include "../../include/dgpmp2_b200.h"
 #include "kernels.cuh"
+#include "host_params.h"
 
 using namespace dgpmp2;
 
@@ -25,6 +26,7 @@ int cuda_fail(cudaError_t e) {
 
 constexpr int kPdlDefault = 1;       // DGPMP2_PDL: 1 = plain launches (default), 2 = programmatic dependent launch of gn_step
 constexpr int kSmemLimit = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
+constexpr int kMpSmemLimit = kSmemLimit - 2048;   // gn_step_mp_kernel also holds ~1.2 KB of static shared memory
 
 int check_params(const dgpmp2_params* p, const dgpmp2_weights* w) {
   if (p == nullptr) return DGPMP2_ERR_ARG;
@@ -41,87 +43,6 @@ int check_params(const dgpmp2_params* p, const dgpmp2_weights* w) {
   if (!(p->res > 0.0) || !(p->dt > 0.0)) return DGPMP2_ERR_ARG;
   if (p->sdf_stride_b < 0) return DGPMP2_ERR_ARG;
   return DGPMP2_OK;
-}
-
-int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  if (e == nullptr) return dflt;
-  const int v = atoi(e);
-  return v > 0 ? v : dflt;
-}
-
-KParams make_kparams(const dgpmp2_params* p) {
-  KParams k;
-  memset(&k, 0, sizeof(k));
-  k.B = p->B; k.T = p->T; k.H = p->H; k.W = p->W; k.flags = p->flags;
-  const int d = 2 * p->dof;
-  // plan_layer.py:39-45
-  k.M = d * ((p->T - 1) + 2) + p->T;
-  if (p->flags & DGPMP2_FLAG_NONHOLONOMIC) k.M += p->T;
-  if (p->flags & DGPMP2_FLAG_VEL_LIMITS) k.M += p->dof * p->T;
-  k.sdf_sb = p->sdf_stride_b;
-  k.res = p->res;
-  k.inv_res = 1.0 / p->res;
-  k.orig_x = 0.0 - p->x_lo / p->res;          // sdf_utils.py:57
-  k.orig_y = 0.0 - p->y_lo / p->res;          // sdf_utils.py:58
-  k.dt = p->dt;
-  k.qa = 12.0 * std::pow(p->dt, -3.0);        // gp_factor.py:66-68
-  k.qb = -6.0 * std::pow(p->dt, -2.0);
-  k.qc = 4.0 * std::pow(p->dt, -1.0);
-  k.r_sphere = p->r_sphere; k.ks = p->ks_inv2; k.kg = p->kg_inv2; k.reg = p->reg;
-  k.kd = p->kd_inv2; k.kv = p->kv_inv2; k.vx_lim = p->vx_lim; k.vy_lim = p->vy_lim;
-  for (int i = 0; i < 9; ++i) { k.qc_const[i] = p->qc_inv[i]; k.qc_fix[i] = p->qc_inv_fix[i]; }
-  k.w_const = p->w_obs; k.w_fix = p->w_obs_fix; k.eps_const = p->eps;
-  // constant GP blocks for the static case: Q = [[qa C, qb C],[qb C, qc C]], Phi = [[I, dt I],[0, I]]
-  const int dof = p->dof;
-  auto kron = [&](const double* C, double* Q) {
-    for (int a = 0; a < dof; ++a)
-      for (int c = 0; c < dof; ++c) {
-        const double v = C[a * dof + c];
-        Q[a * d + c] = k.qa * v;
-        Q[a * d + c + dof] = k.qb * v;
-        Q[(a + dof) * d + c] = k.qb * v;
-        Q[(a + dof) * d + c + dof] = k.qc * v;
-      }
-  };
-  kron(k.qc_const, k.Qs);
-  kron(k.qc_fix, k.Qf);
-  for (int c = 0; c < d; ++c)
-    for (int a = 0; a < dof; ++a) {
-      k.PQs[a * d + c] = k.Qs[a * d + c];
-      k.PQs[(a + dof) * d + c] = k.dt * k.Qs[a * d + c] + k.Qs[(a + dof) * d + c];
-    }
-  for (int a = 0; a < d; ++a)
-    for (int c = 0; c < dof; ++c) {
-      k.PQPs[a * d + c] = k.PQs[a * d + c];
-      k.PQPs[a * d + c + dof] = k.dt * k.PQs[a * d + c] + k.PQs[a * d + c + dof];
-    }
-  k.static_gp = 0;   // set by the caller once the weights are known
-  k.ext_same = 0;
-  bcr_make_plan(p->T, env_int("DGPMP2_TAIL", kTailMaxDefault), env_int("DGPMP2_WIDE", kWideMinDefault), k.plan);
-  return k;
-}
-
-// static_gp: no per-(b,t) Qc^-1 and not Q_FULL.  ext_same: additionally every weight equals its
-// constructor-time value, so err_ext == err.
-template <typename IO>
-void finish_kparams(KParams& k, const KWeights<IO>& kw) {
-  k.static_gp = (kw.qc == nullptr && !(k.flags & DGPMP2_FLAG_Q_FULL)) ? 1 : 0;
-  bool same = k.static_gp && kw.w == nullptr && k.w_const == k.w_fix;
-  for (int i = 0; i < 9 && same; ++i) same = (k.qc_const[i] == k.qc_fix[i]);
-  k.ext_same = same ? 1 : 0;
-}
-
-template <typename IO>
-KWeights<IO> make_kweights(const dgpmp2_weights* w) {
-  KWeights<IO> k;
-  memset(&k, 0, sizeof(k));
-  if (w != nullptr) {
-    k.qc = static_cast<const IO*>(w->qc_inv); k.qc_sb = w->qc_stride_b; k.qc_st = w->qc_stride_t;
-    k.w = static_cast<const IO*>(w->w_obs); k.w_sb = w->w_stride_b; k.w_st = w->w_stride_t;
-    k.eps = static_cast<const IO*>(w->eps); k.e_sb = w->eps_stride_b; k.e_st = w->eps_stride_t;
-  }
-  return k;
 }
 
 struct LaunchShape { int np, tpp, threads, smem, grid; };
@@ -174,7 +95,7 @@ int choose_shape(int B, int T, int mode, LaunchShape& s) {
 
 // Opt a kernel in to > 48 KB of dynamic shared memory, once per (kernel, device).
 template <typename K>
-int allow_smem(K kernel, int bytes) {
+int allow_smem(K kernel, int bytes, int limit = kSmemLimit) {
   if (bytes <= 48 * 1024) return DGPMP2_OK;
   static std::mutex mu;
   static std::vector<std::pair<const void*, int>> done;
@@ -186,7 +107,7 @@ int allow_smem(K kernel, int bytes) {
     for (const auto& e : done)
       if (e.first == key && e.second == dev) return DGPMP2_OK;
   }
-  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit));
   std::lock_guard<std::mutex> lk(mu);
   done.emplace_back(key, dev);
   return DGPMP2_OK;
@@ -222,9 +143,75 @@ int launch_step(const KParams& k, const KWeights<IO>& kw, const IO* th, const IO
   return DGPMP2_OK;
 }
 
+// ---- mixed-precision step (mp.cuh) --------------------------------------------------------------------------------
+// Shape: TPP = ceil32(T) threads per problem (one per node), NP problems per CTA = the SM's share of the batch, bounded
+// by the named barriers (15 problems of more than one warp), the CTA size and shared memory.  CTAs of <= 512 threads
+// run the 128-register instantiation, larger ones the 64-register one.
+struct MpShape { int np, tpp, threads, smem, grid, maxt; };
+
+template <int D>
+int choose_shape_mp(int B, int T, MpShape& s) {
+  const int tpp = (T + 31) / 32 * 32;
+  if (tpp > 1024) return DGPMP2_ERR_UNSUPPORTED;
+  const size_t legacy1 = StepSmem<D, float>::bytes(1, T, 0);      // the in-kernel fp64 path needs its own carve-up
+  if (legacy1 > (size_t)kMpSmemLimit) return DGPMP2_ERR_UNSUPPORTED;
+  const int maxt = env_int("DGPMP2_MP_MAXT", 1024) <= 512 ? 512 : 1024;
+  int np = (B + sm_count() - 1) / sm_count();
+  np = env_int("DGPMP2_NP", np);
+  if (np > B) np = B;
+  const int cap_bar = (tpp == 32) ? kMpMaxNP : 15;
+  if (np > cap_bar) np = cap_bar;
+  if (np * tpp > maxt) np = maxt / tpp;
+  if (np < 1) {
+    if (tpp > maxt) return DGPMP2_ERR_UNSUPPORTED;
+    np = 1;
+  }
+  const size_t per = MpRec<D>::problem_floats(T) * sizeof(float);
+  while (np > 1 && (size_t)np * per > (size_t)kMpSmemLimit) --np;
+  size_t bytes = (size_t)np * per;
+  if (bytes > (size_t)kMpSmemLimit) return DGPMP2_ERR_UNSUPPORTED;
+  if (bytes < legacy1) bytes = legacy1;
+  s.np = np; s.tpp = tpp; s.threads = np * tpp; s.smem = (int)bytes; s.grid = (B + np - 1) / np;
+  s.maxt = (s.threads <= 512) ? 512 : 1024;
+  return DGPMP2_OK;
+}
+
+// DGPMP2_PRECISION=32 routes the fp32-I/O step through the mixed-precision kernel (mp.cuh).  It is opt-in: measured on
+// B200 it is SLOWER than the all-double kernel at every BASELINE shape (profiles/r02_mp_experiment.md) -- fp64 issues at
+// half the fp32 rate on this part, the step is bound by dependent-instruction latency, and the two refinement sweeps
+// the 1e-5 parity bar needs cost more chain length than the fp32 factorisation saves.
+bool mp_enabled() { return env_int("DGPMP2_PRECISION", 64) == 32; }
+
+template <int DOF>
+int launch_step_mp(const KParams& k, const KWeights<float>& kw, const float* th, const float* start, const float* goal,
+                   const float* sdf, float* dth, float* err, float* err_ext, int32_t* status, int32_t* diag,
+                   cudaStream_t st, bool& launched) {
+  constexpr int D = 2 * DOF;
+  launched = false;
+  MpShape s;
+  if (choose_shape_mp<D>(k.B, k.T, s) != DGPMP2_OK) return DGPMP2_OK;   // not applicable: the caller uses the fp64 kernel
+  const int force64 = env_int("DGPMP2_MP_FORCE64", 0) == 1 ? 1 : 0;
+  int rc;
+  if (s.maxt == 512) {
+    auto kern = gn_step_mp_kernel<DOF, 512>;
+    rc = allow_smem(kern, s.smem, kMpSmemLimit);
+    if (rc != DGPMP2_OK) return rc;
+    kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, diag, s.np, s.tpp, force64);
+  } else {
+    auto kern = gn_step_mp_kernel<DOF, 1024>;
+    rc = allow_smem(kern, s.smem, kMpSmemLimit);
+    if (rc != DGPMP2_OK) return rc;
+    kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, diag, s.np, s.tpp, force64);
+  }
+  CUDA_TRY(cudaGetLastError());
+  launched = true;
+  return DGPMP2_OK;
+}
+
 template <typename IO>
 int gn_step_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO* goal, const IO* sdf,
-                 const dgpmp2_weights* w, IO* dth, IO* err, IO* err_ext, int32_t* status, void* stream) {
+                 const dgpmp2_weights* w, IO* dth, IO* err, IO* err_ext, int32_t* status, void* stream,
+                 int32_t* diag = nullptr) {
   int rc = check_params(p, w);
   if (rc != DGPMP2_OK) return rc;
   if (p->B == 0) return DGPMP2_OK;
@@ -233,6 +220,15 @@ int gn_step_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO
   const KWeights<IO> kw = make_kweights<IO>(w);
   finish_kparams(k, kw);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if constexpr (sizeof(IO) == 4) {
+    if (mp_enabled()) {
+      bool launched = false;
+      rc = (p->dof == 2) ? launch_step_mp<2>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, diag, st, launched)
+                         : launch_step_mp<3>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, diag, st, launched);
+      if (rc != DGPMP2_OK || launched) return rc;
+    }
+  }
+  if (diag != nullptr) CUDA_TRY(cudaMemsetAsync(diag, 0, sizeof(int32_t) * (size_t)p->B, st));   // 0 = all-double kernel
   if (p->dof == 2) return launch_step<2, IO>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
   return launch_step<3, IO>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, st);
 }
@@ -467,6 +463,12 @@ int gn_step_host_impl(const dgpmp2_params* p, const IO* th, const IO* start, con
 
 }  // namespace
 
+#ifdef DGPMP2_MP_TIMING
+extern "C" int dgpmp2_debug_mp_clocks(long long* out) {
+  return cudaMemcpyFromSymbol(out, dgpmp2::g_mp_clock, sizeof(long long) * 64) == cudaSuccess ? 0 : -3;
+}
+#endif
+
 #ifdef DGPMP2_TIMING
 extern "C" int dgpmp2_debug_phase_clocks(long long* out) {
   return cudaMemcpyFromSymbol(out, dgpmp2::g_phase_clock, sizeof(long long) * 64) == cudaSuccess ? 0 : -3;
@@ -497,6 +499,11 @@ int dgpmp2_gn_step_f64(const dgpmp2_params* p, const double* th, const double* s
                        const double* sdf, const dgpmp2_weights* w, double* dth, double* err, double* err_ext,
                        int32_t* status, void* stream) {
   return gn_step_impl<double>(p, th, start, goal, sdf, w, dth, err, err_ext, status, stream);
+}
+int dgpmp2_gn_step_diag_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal,
+                            const float* sdf, const dgpmp2_weights* w, float* dth, float* err, float* err_ext,
+                            int32_t* status, int32_t* refine, void* stream) {
+  return gn_step_impl<float>(p, th, start, goal, sdf, w, dth, err, err_ext, status, stream, refine);
 }
 
 int dgpmp2_gn_step_backward_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal,
@@ -607,6 +614,17 @@ int dgpmp2_gn_step_launch_shape(const dgpmp2_params* p, int32_t elem_size, int32
   if (rc != DGPMP2_OK) return rc;
   LaunchShape s{0, 0, 0, 0, 0};
   const int B = p->B > 0 ? p->B : 1;
+  if (elem_size == 4 && mp_enabled()) {
+    MpShape m;
+    rc = (p->dof == 2) ? choose_shape_mp<4>(B, p->T, m) : choose_shape_mp<6>(B, p->T, m);
+    if (rc == DGPMP2_OK) {
+      if (problems_per_cta) *problems_per_cta = m.np;
+      if (threads) *threads = m.threads;
+      if (smem_bytes) *smem_bytes = m.smem;
+      if (grid) *grid = m.grid;
+      return DGPMP2_OK;
+    }
+  }
   if (p->dof == 2) rc = (elem_size == 4) ? choose_shape<4, float>(B, p->T, 0, s) : choose_shape<4, double>(B, p->T, 0, s);
   else rc = (elem_size == 4) ? choose_shape<6, float>(B, p->T, 0, s) : choose_shape<6, double>(B, p->T, 0, s);
   if (rc != DGPMP2_OK) return rc;

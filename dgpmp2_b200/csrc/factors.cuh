@@ -12,8 +12,7 @@
 // branch (pixel floor, hinge test) the operation order of the reference is
 // reproduced so the branch sees bit-identical numbers.
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "hd.cuh"
 #include "bcr_plan.cuh"
 
 namespace dgpmp2 {
@@ -31,12 +30,15 @@ struct KParams {
   // Host-precomputed GP blocks for the static case (no per-(b,t) Qc^-1, not Q_FULL): row-major d x d.
   int static_gp;        // 1: use Qs / PQs / PQPs below instead of building them per state
   int ext_same;         // 1: err_ext == err (static weights equal to the constructor-time ones)
+  int fuse1;            // 1: gn_step_kernel eliminates the level-1 nodes inside the assembly (kernels.cuh: assemble_cta)
   double Qs[36];        // Q^-1 from qc_const
   double PQs[36];       // Phi^T Q^-1
   double PQPs[36];      // Phi^T Q^-1 Phi
   double Qf[36];        // Q^-1 from qc_fix (err_ext)
   // BCR schedule (bcr.cuh: BcrPlan), computed on the host
   BcrPlan plan;
+  // mixed-precision step (mp.cuh): refinement is accepted once the estimated remaining error is below mp_accept * |x|
+  float mp_accept;
 };
 
 template <typename IO>
@@ -48,24 +50,24 @@ struct KWeights {
 
 enum : int { FLAG_NONHOLONOMIC = 1, FLAG_VEL_LIMITS = 2, FLAG_Q_FULL = 4, FLAG_HEAD = 8, FLAG_HEAD_QC_VEC = 16 };
 
-__device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
+DG_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // j <= i
 
-template <typename IO> __device__ __forceinline__ double ldg_d(const IO* p) { return (double)__ldg(p); }
+template <typename IO> DG_HD double ldg_d(const IO* p) { return (double)dg_ldg(p); }
 
 // ---------------------------------------------------------------------------
 // Fused learned-covariance head (diff_gpmp2_planner.py:247-283).  With FLAG_HEAD the weight pointers hold
 // the raw outputs of the learned module; every covariance entry is a product of two of them, rounded once in
 // the I/O element type (what torch.mul gives on the reference's tensors) and then widened.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double io_prod(float a, float b) { return (double)__fmul_rn(a, b); }
-__device__ __forceinline__ double io_prod(double a, double b) { return __dmul_rn(a, b); }
+DG_HD double io_prod(float a, float b) { return (double)dg_fmul(a, b); }
+DG_HD double io_prod(double a, double b) { return dg_dmul(a, b); }
 
 // per-state scalar weight (w_obs, eps): the constant, the given value, or the square of the raw head output
 template <typename IO>
-__device__ __forceinline__ double load_state_weight(const KParams& P, const IO* p, long long sb, long long st,
+DG_HD double load_state_weight(const KParams& P, const IO* p, long long sb, long long st,
                                                     int b, int t, double dflt) {
   if (p == nullptr) return dflt;
-  const IO v = __ldg(p + (long long)b * sb + (long long)t * st);
+  const IO v = dg_ldg(p + (long long)b * sb + (long long)t * st);
   return (P.flags & FLAG_HEAD) ? io_prod(v, v) : (double)v;
 }
 
@@ -77,36 +79,36 @@ struct SdfSample { double dist, Jx, Jy; };   // J as returned by bilinear_interp
 // EXACT_J: divide the gradient by res exactly as the reference does (bilinear_interpolate API, bit-exact J);
 // otherwise multiply by 1/res (<= 1 ulp difference, no branch depends on J) -- used inside the GN kernels.
 template <typename IO, bool EXACT_J = true>
-__device__ __forceinline__ SdfSample sdf_bilinear(const IO* __restrict__ sdf, int H, int W,
+DG_HD SdfSample sdf_bilinear(const IO* __restrict__ sdf, int H, int W,
                                                   double orig_x, double orig_y, double res,
                                                   double x, double y, double inv_res = 0.0) {
   // px = orig_x + x / res ; py = orig_y - y / res   (true divisions, reference order)
-  const double px = __dadd_rn(orig_x, __ddiv_rn(x, res));
-  const double py = __dsub_rn(orig_y, __ddiv_rn(y, res));
+  const double px = dg_dadd(orig_x, dg_ddiv(x, res));
+  const double py = dg_dsub(orig_y, dg_ddiv(y, res));
   // floor -> +1 -> clamp to the image (sdf_utils.py:64-72).  The clamps run on integers: cvt.rmi saturates, so
   // |px| >= 2^31 lands on the same border pixel as the reference's float clamp (a NaN coordinate gives NaN either way)
-  const int ix = __double2int_rd(px), iy = __double2int_rd(py);
-  const int x1 = min(max(ix, 0), W - 1), x2 = min(max(ix, -1), W - 2) + 1;   // clamp(ix + 1, 0, W - 1) without overflow
-  const int y1 = min(max(iy, 0), H - 1), y2 = min(max(iy, -1), H - 2) + 1;
+  const int ix = dg_d2i_rd(px), iy = dg_d2i_rd(py);
+  const int x1 = dg_min(dg_max(ix, 0), W - 1), x2 = dg_min(dg_max(ix, -1), W - 2) + 1;   // clamp(ix + 1, 0, W - 1) without overflow
+  const int y1 = dg_min(dg_max(iy, 0), H - 1), y2 = dg_min(dg_max(iy, -1), H - 2) + 1;
   const double x1d = (double)x1, x2d = (double)x2, y1d = (double)y1, y2d = (double)y2;
   const IO* r1 = sdf + (long long)y1 * W;
   const IO* r2 = sdf + (long long)y2 * W;
   const double v11 = ldg_d(r1 + x1), v21 = ldg_d(r1 + x2);
   const double v12 = ldg_d(r2 + x1), v22 = ldg_d(r2 + x2);
   // weights from the CLAMPED indices (:81-89)
-  const double ax = __dsub_rn(x2d, px), bx = __dsub_rn(px, x1d);
-  const double ay = __dsub_rn(y2d, py), by = __dsub_rn(py, y1d);
+  const double ax = dg_dsub(x2d, px), bx = dg_dsub(px, x1d);
+  const double ay = dg_dsub(y2d, py), by = dg_dsub(py, y1d);
   // dist = wa*v11 + wb*v21 + wc*v12 + wd*v22, separately rounded like the tensor ops (:90)
-  const double wa = __dmul_rn(ax, ay), wb = __dmul_rn(bx, ay), wc = __dmul_rn(ax, by), wd = __dmul_rn(bx, by);
+  const double wa = dg_dmul(ax, ay), wb = dg_dmul(bx, ay), wc = dg_dmul(ax, by), wd = dg_dmul(bx, by);
   SdfSample s;
-  s.dist = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(wa, v11), __dmul_rn(wb, v21)), __dmul_rn(wc, v12)),
-                     __dmul_rn(wd, v22));
+  s.dist = dg_dadd(dg_dadd(dg_dadd(dg_dmul(wa, v11), dg_dmul(wb, v21)), dg_dmul(wc, v12)),
+                     dg_dmul(wd, v22));
   // J[:, :, 0] = -1*(wja*(v21-v11) + wjb*(v22-v12))/res ; J[:, :, 1] = (wjc*(v12-v11) + wjd*(v22-v21))/res  (:93-94)
-  const double gx = __dadd_rn(__dmul_rn(ay, __dsub_rn(v21, v11)), __dmul_rn(by, __dsub_rn(v22, v12)));
-  const double gy = __dadd_rn(__dmul_rn(ax, __dsub_rn(v12, v11)), __dmul_rn(bx, __dsub_rn(v22, v21)));
+  const double gx = dg_dadd(dg_dmul(ay, dg_dsub(v21, v11)), dg_dmul(by, dg_dsub(v22, v12)));
+  const double gy = dg_dadd(dg_dmul(ax, dg_dsub(v12, v11)), dg_dmul(bx, dg_dsub(v22, v21)));
   if (EXACT_J) {
-    s.Jx = __ddiv_rn(-gx, res);
-    s.Jy = __ddiv_rn(gy, res);
+    s.Jx = dg_ddiv(-gx, res);
+    s.Jy = dg_ddiv(gy, res);
   } else {
     s.Jx = -gx * inv_res;
     s.Jy = gy * inv_res;
@@ -116,7 +118,7 @@ __device__ __forceinline__ SdfSample sdf_bilinear(const IO* __restrict__ sdf, in
 
 // Hinge (obstacle_cost.py:30-37): c = (dist <= eps_tot) ? eps_tot - dist : 0 ; H_e = (dist <= eps_tot) ? -J : 0
 struct ObsTerm { double c, hx, hy; };
-__device__ __forceinline__ ObsTerm hinge(const SdfSample& s, double eps_tot) {
+DG_HD ObsTerm hinge(const SdfSample& s, double eps_tot) {
   ObsTerm o;
   const bool active = s.dist <= eps_tot;
   o.c = active ? (eps_tot - s.dist) : 0.0;
@@ -129,14 +131,14 @@ __device__ __forceinline__ ObsTerm hinge(const SdfSample& s, double eps_tot) {
 // GP prior inverse covariance for factor i (gp_factor.py:65-73) or given in full (plan_layer.py:90)
 // ---------------------------------------------------------------------------
 template <int DOF, typename IO>
-__device__ __forceinline__ void load_qinv(const KParams& P, const KWeights<IO>& Wt, int b, int i, double (&Q)[2 * DOF][2 * DOF]) {
+DG_HD void load_qinv(const KParams& P, const KWeights<IO>& Wt, int b, int i, double (&Q)[2 * DOF][2 * DOF]) {
   constexpr int D = 2 * DOF;
   if (P.flags & FLAG_Q_FULL) {
     const IO* q = Wt.qc + (long long)b * Wt.qc_sb + (long long)i * Wt.qc_st;
     if (P.flags & FLAG_HEAD) {          // 'q_full' head: Q^-1 = v v^T, v = d raw values (:274-278)
       IO v[D];
 #pragma unroll
-      for (int a = 0; a < D; ++a) v[a] = __ldg(q + a);
+      for (int a = 0; a < D; ++a) v[a] = dg_ldg(q + a);
 #pragma unroll
       for (int a = 0; a < D; ++a)
 #pragma unroll
@@ -155,13 +157,13 @@ __device__ __forceinline__ void load_qinv(const KParams& P, const KWeights<IO>& 
     if (P.flags & FLAG_HEAD_QC_VEC) {   // 'qc_full' head: Qc^-1 = v v^T, v = dof raw values (:269-273)
       IO v[DOF];
 #pragma unroll
-      for (int a = 0; a < DOF; ++a) v[a] = __ldg(q + a);
+      for (int a = 0; a < DOF; ++a) v[a] = dg_ldg(q + a);
 #pragma unroll
       for (int a = 0; a < DOF; ++a)
 #pragma unroll
         for (int c = 0; c < DOF; ++c) C[a][c] = io_prod(v[a], v[c]);
     } else {                            // 'diag_identity' head: Qc^-1 = q^2 I (:256-262)
-      const IO v = __ldg(q);
+      const IO v = dg_ldg(q);
       const double qq = io_prod(v, v);
 #pragma unroll
       for (int a = 0; a < DOF; ++a)
@@ -192,7 +194,7 @@ __device__ __forceinline__ void load_qinv(const KParams& P, const KWeights<IO>& 
 }
 
 template <int DOF>
-__device__ __forceinline__ void fixed_qinv(const KParams& P, double (&Q)[2 * DOF][2 * DOF]) {
+DG_HD void fixed_qinv(const KParams& P, double (&Q)[2 * DOF][2 * DOF]) {
 #pragma unroll
   for (int a = 0; a < DOF; ++a)
 #pragma unroll
@@ -207,7 +209,7 @@ __device__ __forceinline__ void fixed_qinv(const KParams& P, double (&Q)[2 * DOF
 
 // g = th_next - Phi th   (gp_factor.py:105), Phi = [[I, dt I],[0, I]]
 template <int DOF>
-__device__ __forceinline__ void gp_residual(const double (&th)[2 * DOF], const double (&thn)[2 * DOF], double dt,
+DG_HD void gp_residual(const double (&th)[2 * DOF], const double (&thn)[2 * DOF], double dt,
                                             double (&g)[2 * DOF]) {
 #pragma unroll
   for (int a = 0; a < DOF; ++a) {
@@ -217,7 +219,7 @@ __device__ __forceinline__ void gp_residual(const double (&th)[2 * DOF], const d
 }
 
 template <int D>
-__device__ __forceinline__ double quad_form(const double (&Q)[D][D], const double (&g)[D]) {
+DG_HD double quad_form(const double (&Q)[D][D], const double (&g)[D]) {
   double s = 0.0;
 #pragma unroll
   for (int a = 0; a < D; ++a) {
@@ -245,7 +247,7 @@ struct NodeOut {
 
 // th_prev / th_next are ignored at the trajectory ends.
 template <int DOF, typename IO>
-__device__ __forceinline__ void assemble_node(const KParams& P, const KWeights<IO>& Wt, int b, int t,
+DG_HD void assemble_node(const KParams& P, const KWeights<IO>& Wt, int b, int t,
                                               const double (&thp)[2 * DOF], const double (&th)[2 * DOF],
                                               const double (&thn)[2 * DOF],
                                               const IO* __restrict__ start_b, const IO* __restrict__ goal_b,
@@ -403,7 +405,7 @@ __device__ __forceinline__ void assemble_node(const KParams& P, const KWeights<I
   {
     const double eps = load_state_weight<IO>(P, Wt.eps, Wt.e_sb, Wt.e_st, b, t, P.eps_const);
     const double w = load_state_weight<IO>(P, Wt.w, Wt.w_sb, Wt.w_st, b, t, P.w_const);
-    const double eps_tot = __dadd_rn(eps, P.r_sphere);
+    const double eps_tot = dg_dadd(eps, P.r_sphere);
     const SdfSample s = sdf_bilinear<IO, false>(sdf_b, P.H, P.W, P.orig_x, P.orig_y, P.res, th[0], th[1], P.inv_res);
     const ObsTerm ob = hinge(s, eps_tot);
     o.Dm[0][0] += w * ob.hx * ob.hx;
@@ -423,7 +425,7 @@ __device__ __forceinline__ void assemble_node(const KParams& P, const KWeights<I
     if (P.flags & FLAG_NONHOLONOMIC) {
       // nonholonomic_factor.py:16-30, state (x, y, h, vx, vy, w); Jacobian row reproduced literally
       double sh, ch;
-      sincos(th[2], &sh, &ch);
+      dg_sincos(th[2], &sh, &ch);
       const double e = th[4] * ch - th[3] * sh;
       double n[D] = {0.0, 0.0, -th[4] * sh + th[3] * ch, -sh, ch, 0.0};
 #pragma unroll
@@ -455,6 +457,7 @@ __device__ __forceinline__ void assemble_node(const KParams& P, const KWeights<I
 
 }  // namespace dgpmp2
 
+#ifdef __CUDACC__   // (device-only from here on; the forward part above also compiles for the host emulator of the tests)
 // ===========================================================================
 // Backward of one GN step (reverse-mode derivative of dtheta = Lambda^-1 R and of err_ext).
 //
@@ -661,3 +664,4 @@ __device__ __forceinline__ void backward_node(const KParams& P, const KWeights<I
 }
 
 }  // namespace dgpmp2
+#endif  // __CUDACC__

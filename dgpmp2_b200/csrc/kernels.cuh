@@ -15,6 +15,7 @@
 namespace dgpmp2 { __device__ void g_phase_clock_fwd(int i); }
 #endif
 #include "bcr.cuh"
+#include "mp.cuh"
 
 namespace dgpmp2 {
 
@@ -55,8 +56,7 @@ struct StepSmem {
 // Assemble the CTA's np * T nodes (one thread per node record, records enumerated problem-major
 // in slot order) from the staged trajectory.
 //
-// fuse1 (experimental, compiled only with -DDGPMP2_EXPERIMENTAL_FUSE1; uniform; requires P.static_gp and at least
-// one elimination level): the thread of a level-1 node (odd state j) eliminates it straight from its registers
+// fuse1 (uniform; requires P.static_gp and at least one elimination level; gn_step_kernel only): the thread of a level-1 node (odd state j) eliminates it straight from its registers
 // -- L_j, F_j = L^-1 U_j, g_j = L^-1 r_j and E_j = L^-1 U_{j-1}^T with U_{j-1} = -Phi^T Q^-1, a host-known constant in
 // the static-GP case -- and writes the record once in its eliminated form; bcr_solve then skips the level-1
 // elimination phase and its barrier.  Same arithmetic on the same doubles as bcr_elim_level: bit-identical results.
@@ -85,7 +85,6 @@ __device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO
     assemble_node<DOF, IO>(P, Wt, b, t, thp, thc, thn, start + (size_t)b * D, goal + (size_t)b * D,
                            sdf + (size_t)b * P.sdf_sb, o);
     double* nd = S.nodes + (size_t)p * N::problem_stride(T) + (size_t)slot * N::kStride;
-#ifdef DGPMP2_EXPERIMENTAL_FUSE1
     if (fuse1 && slot < P.plan.lv[0].ne) {          // level-1 node: the slots [0, ne) of level order
       constexpr int DS = N::DS;
       double L[DS];
@@ -116,7 +115,6 @@ __device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO
       sts2(nd + N::oX, o.err, o.err_ext);
       continue;
     }
-#endif
 #pragma unroll
     for (int a = 0; a < D; ++a) {
       st_vec<D>(nd + N::oD + a * D, o.Dm[a]);
@@ -203,6 +201,34 @@ __device__ void g_phase_clock_fwd(int i) { g_phase_clock[i] = clock64(); }
 #define DGPMP2_STAMP(i) do { } while (0)
 #endif
 
+// dth (natural order -> coalesced stores), err / err_ext (one deterministic warp reduction per problem), status
+template <int DOF, typename IO>
+__device__ __forceinline__ void step_epilogue(const KParams& P, const StepSmem<2 * DOF, IO>& S, int T, int b0, int np,
+                                              IO* __restrict__ dth, IO* __restrict__ err, IO* __restrict__ err_ext,
+                                              int* __restrict__ status) {
+  constexpr int D = 2 * DOF;
+  using N = Node<D>;
+  {
+    IO* dst = dth + (size_t)b0 * T * D;
+    const int n = np * T;
+    const float inv_T = P.plan.inv_T;
+    const bool vec = (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0ull;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int p = fast_div(i, inv_T), t = i - p * T;
+      double x[D];
+      ld_vec<D>(S.nodes + (size_t)p * N::problem_stride(T) + (size_t)bcr_slot(T, t) * N::kStride + N::oR, x);
+      store_state<D, IO>(dst + (size_t)i * D, x, vec);
+    }
+  }
+  const double invM = 1.0 / (double)P.M;
+  reduce2_per_problem(S.nodes + N::oX, N::kStride, N::problem_stride(T), np, T, [&](int p, double s0, double s1) {
+    err[b0 + p] = (IO)(s0 * invM);
+    err_ext[b0 + p] = (IO)(s1 * invM);
+  });
+  if (status != nullptr)
+    for (int p = threadIdx.x; p < np; p += blockDim.x) status[b0 + p] = S.fail[p];
+}
+
 // One fused Gauss-Newton iteration.  grid = ceil(B / NP), block = NP * TPP threads (rounded to a warp).
 template <int DOF, typename IO>
 __global__ void __launch_bounds__(DOF == 2 ? 512 : 256)
@@ -228,11 +254,7 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
   __syncthreads();
   DGPMP2_STAMP(1);
 
-#ifdef DGPMP2_EXPERIMENTAL_FUSE1
-  const bool fuse1 = P.static_gp != 0 && P.plan.nl >= 1;      // uniform
-#else
-  constexpr bool fuse1 = false;
-#endif
+  const bool fuse1 = P.fuse1 != 0;      // uniform (host: static GP blocks and at least one elimination level)
   assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf, fuse1);
   __syncthreads();
   DGPMP2_STAMP(2);
@@ -240,26 +262,119 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
   bcr_solve<D>(S.nodes, P.plan, T, np, S.fail, fuse1);   // ends with a barrier
   DGPMP2_STAMP(3);
 
-  {  // dth, natural order -> coalesced stores
-    IO* dst = dth + (size_t)b0 * T * D;
-    const int n = np * T;
-    const float inv_T = P.plan.inv_T;
-    const bool vec = (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0ull;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int p = fast_div(i, inv_T), t = i - p * T;
-      double x[D];
-      ld_vec<D>(S.nodes + (size_t)p * N::problem_stride(T) + (size_t)bcr_slot(T, t) * N::kStride + N::oR, x);
-      store_state<D, IO>(dst + (size_t)i * D, x, vec);
+  step_epilogue<DOF, IO>(P, S, T, b0, np, dth, err, err_ext, status);
+  DGPMP2_STAMP(4);
+}
+
+// ---------------------------------------------------------------------------
+// Mixed-precision GN step (mp.cuh): fp32 node-owner block cyclic reduction + fp64 residual refinement, one thread per
+// trajectory state, TPP = ceil32(T) threads per problem, NP problems per CTA, each problem on its own named barrier.
+// Problems whose fp32 factorisation breaks down or whose refinement does not contract are redone, inside this
+// launch, by the fp64 path of gn_step_kernel (one at a time: rare by construction).
+// ---------------------------------------------------------------------------
+constexpr int kMpMaxNP = 32;
+
+struct MpDevCtx {
+  int bar_id, tpp, lane, wip, nwp;
+  double* errw;   // [2 * nwp], this problem's per-warp error partials
+  int* norm;      // [4], this problem's double-buffered norm maxima
+  int* need64;    // this problem's flag
+  __device__ __forceinline__ void psync() const {
+    if (tpp == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(tpp) : "memory");
+  }
+  __device__ __forceinline__ void sum2(double& a, double& b) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (nwp > 1) {
+      if (lane == 0) { errw[2 * wip] = a; errw[2 * wip + 1] = b; }
+      psync();
+      a = 0.0; b = 0.0;
+      for (int w = 0; w < nwp; ++w) { a += errw[2 * w]; b += errw[2 * w + 1]; }
     }
   }
-  const double invM = 1.0 / (double)P.M;
-  reduce2_per_problem(S.nodes + N::oX, N::kStride, N::problem_stride(T), np, T, [&](int p, double s0, double s1) {
-    err[b0 + p] = (IO)(s0 * invM);
-    err_ext[b0 + p] = (IO)(s1 * invM);
-  });
-  if (status != nullptr)
-    for (int p = threadIdx.x; p < np; p += blockDim.x) status[b0 + p] = S.fail[p];
-  DGPMP2_STAMP(4);
+  __device__ __forceinline__ void max2(int& a, int& b, int it) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a = max(a, __shfl_xor_sync(0xffffffffu, a, o));
+      b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if (nwp == 1) { psync(); return; }
+    int* buf = norm + 2 * (it & 1);
+    if (lane == 0) { atomicMax(buf, a); atomicMax(buf + 1, b); }
+    psync();
+    a = buf[0]; b = buf[1];
+    if (wip == 0 && lane == 0) { int* o = norm + 2 * ((it + 1) & 1); o[0] = 0; o[1] = 0; }
+  }
+  __device__ __forceinline__ void flag64() const { *need64 = 1; }
+#ifdef DGPMP2_MP_TIMING
+  __device__ __forceinline__ void stamp(int i) const;
+#endif
+};
+#ifdef DGPMP2_MP_TIMING
+// Debug builds only (-DDGPMP2_MP_TIMING=cta+1): clock64() stamps of the phases of mp_thread_program, thread 0 of one CTA.
+__device__ long long g_mp_clock[64];
+__device__ __forceinline__ void MpDevCtx::stamp(int i) const {
+  if (blockIdx.x == (DGPMP2_MP_TIMING - 1) && threadIdx.x == 0 && i < 64) g_mp_clock[i] = clock64();
+}
+#endif
+
+template <int DOF, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+gn_step_mp_kernel(const KParams P, const KWeights<float> Wt, const float* __restrict__ th, const float* __restrict__ start,
+                  const float* __restrict__ goal, const float* __restrict__ sdf, float* __restrict__ dth,
+                  float* __restrict__ err, float* __restrict__ err_ext, int* __restrict__ status, int* __restrict__ diag,
+                  const int NP, const int TPP, const int force64) {
+  constexpr int D = 2 * DOF;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_need64[kMpMaxNP];
+  __shared__ int s_norm[kMpMaxNP][4];
+  __shared__ double s_errw[32][2];
+  const int T = P.T;
+  const int p = threadIdx.x / TPP, m = threadIdx.x - p * TPP;
+  const int b0 = blockIdx.x * NP;
+  const int np = min(NP, P.B - b0);
+  if (threadIdx.x < kMpMaxNP) {
+    s_need64[threadIdx.x] = 0;
+    s_norm[threadIdx.x][0] = 0; s_norm[threadIdx.x][1] = 0; s_norm[threadIdx.x][2] = 0; s_norm[threadIdx.x][3] = 0;
+  }
+  __syncthreads();
+  if (p < np) {
+    MpDevCtx cx;
+    cx.bar_id = 1 + p; cx.tpp = TPP; cx.lane = threadIdx.x & 31; cx.wip = m >> 5; cx.nwp = TPP >> 5;
+    cx.errw = &s_errw[(p * TPP) >> 5][0];
+    cx.norm = s_norm[p];
+    cx.need64 = &s_need64[p];
+    float* recs = reinterpret_cast<float*>(smem_raw) + (size_t)p * MpRec<D>::problem_floats(T);
+    // Which of the problem's warps holds which 32 slots rotates with the problem index: the LAST slots are the deep
+    // levels -- the warp that works through most of the solve -- and warp w of a CTA issues on SM sub-partition w % 4,
+    // so without the rotation the deep warps of all problems pile up on one or two of the four schedulers.
+    const int rot = (cx.nwp == 2) ? ((p >> 1) & 1) : (p % cx.nwp);
+    int ms = m + 32 * rot;
+    if (ms >= TPP) ms -= TPP;
+    cx.wip = ms >> 5;   // error partials are summed in slot order, wherever the problem sits in the CTA
+    mp_thread_program<DOF, (DOF == 2), MpDevCtx>(cx, P, Wt, b0 + p, ms, ms < T, th, start, goal, sdf, recs, dth, err, err_ext,
+                                                 diag, force64);
+  }
+  __syncthreads();
+  if (status != nullptr && threadIdx.x < np && !s_need64[threadIdx.x]) status[b0 + threadIdx.x] = 0;
+  // fp64 path for the flagged problems (uniform: every thread reads the same flags)
+  for (int q = 0; q < np; ++q) {
+    if (!s_need64[q]) continue;
+    StepSmem<D, float> S;
+    S.carve(smem_raw, 1, T, 0);
+    const int b = b0 + q;
+    cta_prologue<D, float>(P, S, T, 1, 1, th + (size_t)b * T * D, false);
+    __syncthreads();
+    assemble_cta<DOF, float>(P, Wt, S, b, 1, start, goal, sdf);
+    __syncthreads();
+    bcr_solve<D>(S.nodes, P.plan, T, 1, S.fail);   // ends with a barrier
+    step_epilogue<DOF, float>(P, S, T, b, 1, dth, err, err_ext, status);
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------

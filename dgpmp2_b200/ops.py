@@ -99,6 +99,25 @@ def gn_step(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None,
     return dth, err, err_ext, status
 
 
+def gn_step_diag(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, head=None):
+    """gn_step (float32 I/O) that also reports how the mixed-precision kernel solved each problem:
+    returns dth, err, err_ext, status, refine (B,) int32 -- k > 0: accepted after k refinement iterations,
+    k < 0: handed to the all-double path, 0: the launch used the all-double kernel."""
+    th, start, goal, sdf = _common(p, th, start, goal, sdf)
+    if th.dtype != torch.float32:
+        raise TypeError('gn_step_diag is a float32 entry point')
+    B, T, d = th.shape
+    dth = torch.empty_like(th)
+    err = torch.empty(B, dtype=th.dtype, device=th.device)
+    err_ext = torch.empty_like(err)
+    status = torch.empty(B, dtype=torch.int32, device=th.device)
+    refine = torch.empty(B, dtype=torch.int32, device=th.device)
+    wref, keep = _weights(p, th.dtype, qc_inv, w_obs, eps, B, T, head)
+    check(load().dgpmp2_gn_step_diag_f32(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(sdf), wref, ptr(dth),
+                                          ptr(err), ptr(err_ext), ptr(status), ptr(refine), stream_ptr()))
+    return dth, err, err_ext, status, refine
+
+
 def gn_step_backward(p: CParams, th, start, goal, sdf, dth, g_dth, g_err_ext=None, qc_inv=None, w_obs=None, eps=None,
                      need_th=True, need_start=False, need_goal=False, need_qc=False, need_w=False, need_eps=False,
                      need_sdf=False, head=None):

@@ -17,7 +17,9 @@
  * binding a maintainer of the reference would add.
  *
  * Suffix _f32 / _f64 = element type of the trajectory / SDF / weight / output
- * buffers ("I/O type").  Arithmetic is IEEE double inside every kernel for both
+ * buffers ("I/O type").  Factor evaluation, right-hand sides, errors and residuals are IEEE
+ * double inside every kernel; dgpmp2_gn_step_f32 factorises in fp32 and refines with double
+ * residuals (falling back per problem to the all-double solver), everything else solves in double
  * ("numerics").
  */
 #ifndef DGPMP2_B200_H
@@ -121,6 +123,17 @@ int dgpmp2_gn_step_f32(const dgpmp2_params* p, const float* th, const float* sta
 int dgpmp2_gn_step_f64(const dgpmp2_params* p, const double* th, const double* start, const double* goal,
                        const double* sdf, const dgpmp2_weights* w,
                        double* dth, double* err, double* err_ext, int32_t* status, void* stream);
+
+/*
+ * dgpmp2_gn_step_f32 with one more output for tests / benchmarks: refine (B) int32 tells how each problem was
+ * solved by the mixed-precision kernel (fp32 block cyclic reduction + fp64 residual refinement):
+ *   k > 0  accepted after k refinement iterations,  k < 0  handed to the all-double path after |k| iterations,
+ *   0      the launch used the all-double kernel for every problem (DGPMP2_PRECISION=64, or a shape the
+ *          mixed-precision kernel does not take).
+ */
+int dgpmp2_gn_step_diag_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal,
+                            const float* sdf, const dgpmp2_weights* w,
+                            float* dth, float* err, float* err_ext, int32_t* status, int32_t* refine, void* stream);
 
 /*
  * Backward (reverse-mode derivative) of dgpmp2_gn_step_* -- replaces autograd through the

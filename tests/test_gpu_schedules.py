@@ -68,3 +68,31 @@ def test_every_problem_solves_its_normal_equations(sched, dof):
             os.environ.pop(k, None)
             if saved[k] is not None:
                 os.environ[k] = saved[k]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+def test_level1_elimination_fused_into_the_assembly_is_bit_identical(dtype):
+    """Static-GP launches eliminate the level-1 nodes inside the assembly (kernels.cuh: assemble_cta, fuse1): the same
+    arithmetic on the same doubles as the separate elimination phase (DGPMP2_FUSE1=2) -> identical bits."""
+    from dgpmp2_b200 import ops
+    from dgpmp2_b200.datasets.synthetic import make_problems
+    from tests.gpu_helpers import cparams
+    saved = os.environ.pop('DGPMP2_FUSE1', None)
+    try:
+        for dof, B, T in ((2, 1, 64), (2, 7, 64), (2, 1024, 64), (2, 300, 101), (2, 512, 128), (2, 5, 3), (2, 9, 2),
+                          (3, 64, 96), (3, 3, 12)):
+            base = XYH if dof == 3 else YAML
+            pr = make_problems(B, T, dof=dof, im_size=64, seed=B + T, unique_envs=8, dtype=dtype)
+            th, start, goal, sdf = (pr[k].cuda() for k in ('th_init', 'start', 'goal', 'sdf'))
+            cp = cparams(T, base=base, dof=dof, non_holonomic=(dof == 3))
+            th = ops.gn_solve(cp, th, start, goal, sdf, 3, 0.0)[0]
+            os.environ.pop('DGPMP2_FUSE1', None)
+            a = ops.gn_step(cp, th, start, goal, sdf)
+            os.environ['DGPMP2_FUSE1'] = '2'
+            b = ops.gn_step(cp, th, start, goal, sdf)
+            for x, y in zip(a, b):
+                assert torch.equal(x, y), (dof, B, T)
+    finally:
+        os.environ.pop('DGPMP2_FUSE1', None)
+        if saved is not None:
+            os.environ['DGPMP2_FUSE1'] = saved

@@ -57,14 +57,37 @@ def test_argument_checking_without_a_gpu():
 def test_launch_shape_and_limits():
     from dgpmp2_b200 import _lib, ops
     mk = lambda T, dof=2, B=1024: _lib.make_params(B, T, dof, 16, 16, (-5, 5), (-5, 5), 10.0, 0.4, 0.01, 0.01, 0.1, torch.eye(dof), 0.01, 0.4)
-    s = ops.launch_shape(mk(64))
-    # the ceil(1024 / 148) = 7 problems an SM has to process share ONE CTA (packed BCR items), 147 CTAs on 148 SMs
+    f64 = torch.float64
+    s = ops.launch_shape(mk(64), f64)
+    # all-double kernel (float64 I/O): the ceil(1024 / 148) = 7 problems an SM has to process share ONE CTA
+    # (packed BCR items), 147 CTAs on 148 SMs
     assert s['problems_per_cta'] == 7 and s['grid'] == 147 and s['threads'] == 448
     assert s['smem_bytes'] <= 232448
-    assert ops.launch_shape(mk(64, B=8))['problems_per_cta'] == 1   # small batches: one problem per CTA, 4 lanes per item
-    assert ops.launch_shape(mk(64, B=8))['threads'] == 128
-    assert ops.launch_shape(mk(128))['problems_per_cta'] == 4       # bounded by shared memory (7 would not fit)
-    assert ops.launch_shape(mk(96, dof=3, B=512))['problems_per_cta'] == 2
+    assert ops.launch_shape(mk(64, B=8), f64)['problems_per_cta'] == 1   # small batches: one problem per CTA, 4 lanes per item
+    assert ops.launch_shape(mk(64, B=8), f64)['threads'] == 128
+    assert ops.launch_shape(mk(128), f64)['problems_per_cta'] == 3       # bounded by shared memory (7 would not fit)
+    assert ops.launch_shape(mk(96, dof=3, B=512), f64)['problems_per_cta'] == 2
+    assert ops.launch_shape(mk(500), f64)['smem_bytes'] <= 232448
+    # float32 I/O uses the same kernel by default (the staged trajectory is half as large)
+    assert ops.launch_shape(mk(64))['problems_per_cta'] == 7 and ops.launch_shape(mk(128))['problems_per_cta'] == 4
+    # opt-in mixed-precision kernel (DGPMP2_PRECISION=32): one thread per state, ceil32(T) threads per problem, fp32
+    # records of 208 (d = 4) / 456 (d = 6) bytes per state -> the SM's whole share fits one CTA for every BASELINE config
+    import os
+    saved = os.environ.get('DGPMP2_PRECISION')
+    os.environ['DGPMP2_PRECISION'] = '32'
+    try:
+        s = ops.launch_shape(mk(64))
+        assert s['problems_per_cta'] == 7 and s['grid'] == 147 and s['threads'] == 448 and s['smem_bytes'] <= 232448
+        assert ops.launch_shape(mk(64, B=8))['threads'] == 64
+        s = ops.launch_shape(mk(128))
+        assert s['problems_per_cta'] == 7 and s['threads'] == 896 and s['grid'] == 147
+        s = ops.launch_shape(mk(96, dof=3, B=512))
+        assert s['problems_per_cta'] == 4 and s['threads'] == 384 and s['grid'] == 128
+        assert ops.launch_shape(mk(33, B=100000))['problems_per_cta'] == 15   # one named barrier per problem
+    finally:
+        os.environ.pop('DGPMP2_PRECISION', None)
+        if saved is not None:
+            os.environ['DGPMP2_PRECISION'] = saved
     assert ops.launch_shape(mk(512))['smem_bytes'] <= 232448
     with pytest.raises(_lib.Dgpmp2Error):
         ops.launch_shape(mk(600))             # longer than the on-chip band: documented limit
