@@ -67,6 +67,8 @@ PROTOTYPES = {
     'dgpmp2_gn_solve_f64': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     'dgpmp2_errors_f32': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp, _vp],
     'dgpmp2_errors_f64': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp, _vp],
+    'dgpmp2_errors_backward_f32': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp, _vp],
+    'dgpmp2_errors_backward_f64': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp, _vp],
     'dgpmp2_factors_f32': [_P(CParams), _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp, _vp],
     'dgpmp2_factors_f64': [_P(CParams), _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp, _vp],
     'dgpmp2_sdf_lookup_f32': [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _f64, _f64, _f64, _vp, _vp, _vp],

@@ -303,6 +303,14 @@ int gn_step_backward_impl(const dgpmp2_params* p, const IO* th, const IO* start,
                            g_sdf, p->sdf_stride_b, st);
 }
 
+int grid_for(long long n, int threads) {
+  long long g = (n + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
 template <typename IO>
 int errors_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO* goal, const IO* sdf,
                 const dgpmp2_weights* w, IO* err, IO* err_ext, IO* err_sg, IO* err_gp, IO* err_obs, void* stream) {
@@ -324,12 +332,25 @@ int errors_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO*
   return DGPMP2_OK;
 }
 
-int grid_for(long long n, int threads) {
-  long long g = (n + threads - 1) / threads;
-  const long long cap = 148LL * 16;
-  if (g > cap) g = cap;
-  if (g < 1) g = 1;
-  return (int)g;
+
+template <typename IO>
+int errors_backward_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO* goal, const IO* sdf,
+                         const dgpmp2_weights* w, const IO* g_ext, const IO* g_sg, const IO* g_gp, const IO* g_obs,
+                         IO* g_th, void* stream) {
+  dgpmp2_params q = *p;
+  q.flags &= ~DGPMP2_FLAG_Q_FULL;   // only the constructor-time GP covariance (err_ext) and eps are read
+  int rc = check_params(&q, w);
+  if (rc != DGPMP2_OK) return rc;
+  if (p->B == 0) return DGPMP2_OK;
+  if (!th || !start || !goal || !sdf || !g_th) return DGPMP2_ERR_ARG;
+  const KParams k = make_kparams(&q);
+  const KWeights<IO> kw = make_kweights<IO>(w);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int g = grid_for((long long)p->B * p->T, 256);
+  if (p->dof == 2) errors_bwd_kernel<2, IO><<<g, 256, 0, st>>>(k, kw, th, start, goal, sdf, g_ext, g_sg, g_gp, g_obs, g_th);
+  else errors_bwd_kernel<3, IO><<<g, 256, 0, st>>>(k, kw, th, start, goal, sdf, g_ext, g_sg, g_gp, g_obs, g_th);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
 }
 
 template <typename IO>
@@ -545,6 +566,20 @@ int dgpmp2_errors_f64(const dgpmp2_params* p, const double* th, const double* st
                       const double* sdf, const dgpmp2_weights* w, double* err, double* err_ext, double* err_sg,
                       double* err_gp, double* err_obs, void* stream) {
   return errors_impl<double>(p, th, start, goal, sdf, w, err, err_ext, err_sg, err_gp, err_obs, stream);
+}
+
+int dgpmp2_errors_backward_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal,
+                               const float* sdf, const dgpmp2_weights* w, const float* g_err_ext, const float* g_err_sg,
+                               const float* g_err_gp, const float* g_err_obs, float* g_th, void* stream) {
+  if (p == nullptr) return DGPMP2_ERR_ARG;
+  return errors_backward_impl<float>(p, th, start, goal, sdf, w, g_err_ext, g_err_sg, g_err_gp, g_err_obs, g_th, stream);
+}
+int dgpmp2_errors_backward_f64(const dgpmp2_params* p, const double* th, const double* start, const double* goal,
+                               const double* sdf, const dgpmp2_weights* w, const double* g_err_ext,
+                               const double* g_err_sg, const double* g_err_gp, const double* g_err_obs, double* g_th,
+                               void* stream) {
+  if (p == nullptr) return DGPMP2_ERR_ARG;
+  return errors_backward_impl<double>(p, th, start, goal, sdf, w, g_err_ext, g_err_sg, g_err_gp, g_err_obs, g_th, stream);
 }
 
 int dgpmp2_factors_f32(const dgpmp2_params* p, const float* th, const float* sdf, const dgpmp2_weights* w, float* gp_err,

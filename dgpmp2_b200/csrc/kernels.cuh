@@ -629,6 +629,107 @@ errors_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th,
 }
 
 // ---------------------------------------------------------------------------
+// Backward of the factor sweep: d(err_ext, err_sg, err_gp, err_obs) / d th for given upstream gradients (one scalar
+// per problem and error; NULL = not requested).  The reference gets these from autograd through error_ext_batch /
+// gp_error / obs_error / start_goal_error (plan_layer.py:310-388) -- its training loss is built from them
+// (learning/train_planner.py:327-346).  err itself is computed under no_grad there (:275) and has no gradient.
+// One thread per state; every factor touching state t contributes (priors, GP factors t-1 and t, obstacle, custom).
+// ---------------------------------------------------------------------------
+template <int DOF, typename IO>
+__global__ void __launch_bounds__(256)
+errors_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th, const IO* __restrict__ start,
+                  const IO* __restrict__ goal, const IO* __restrict__ sdf, const IO* __restrict__ g_ext,
+                  const IO* __restrict__ g_sg, const IO* __restrict__ g_gp, const IO* __restrict__ g_obs,
+                  IO* __restrict__ g_th) {
+  constexpr int D = 2 * DOF;
+  const int T = P.T;
+  const long long n = (long long)P.B * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / T), t = (int)(i - (long long)b * T);
+    double thp[D], thc[D], thn[D], g[D];
+    load_state3<DOF, IO>(th + (size_t)b * T * D, T, t, thp, thc, thn);
+#pragma unroll
+    for (int a = 0; a < D; ++a) g[a] = 0.0;
+    const double invM = 1.0 / (double)P.M;
+    const double ge = (g_ext != nullptr) ? ldg_d(g_ext + b) * invM : 0.0;     // err_ext = sum / M
+    const double gs = (g_sg != nullptr) ? ldg_d(g_sg + b) : 0.0;
+    const double gg = (g_gp != nullptr) ? ldg_d(g_gp + b) / (double)(T - 1) : 0.0;
+    const double go = (g_obs != nullptr) ? ldg_d(g_obs + b) / (double)T : 0.0;
+    // priors: e = mean - th  ->  d(0.5 k |e|^2) / d th = -k e
+    if (t == 0 || t == T - 1) {
+      const double k = (t == 0) ? P.ks : P.kg;
+      const IO* mean = ((t == 0) ? start : goal) + (size_t)b * D;
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        const double e = ldg_d(mean + a) - thc[a];
+        g[a] -= (ge * k + gs) * e;
+      }
+    }
+    // GP factors: g_i = th_{i+1} - Phi th_i ; err_ext uses the constructor-time Q^-1, err_gp the identity
+    double Qf[D][D];
+    fixed_qinv<DOF>(P, Qf);
+    if (t < T - 1) {          // factor t: d g_t / d th_t = -Phi
+      double r[D], u[D];
+      gp_residual<DOF>(thc, thn, P.dt, r);
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) s += 0.5 * (Qf[a][c] + Qf[c][a]) * r[c];
+        u[a] = ge * s + gg * r[a];
+      }
+#pragma unroll
+      for (int a = 0; a < DOF; ++a) {
+        g[a] -= u[a];
+        g[a + DOF] -= P.dt * u[a] + u[a + DOF];
+      }
+    }
+    if (t > 0) {              // factor t-1: d g_{t-1} / d th_t = I
+      double r[D];
+      gp_residual<DOF>(thp, thc, P.dt, r);
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) s += 0.5 * (Qf[a][c] + Qf[c][a]) * r[c];
+        g[a] += ge * s + gg * r[a];
+      }
+    }
+    // obstacle: c = eps_tot - dist when active, d c / d (x, y) = -grad dist = -(hx, hy)
+    {
+      const double eps = load_state_weight<IO>(P, Wt.eps, Wt.e_sb, Wt.e_st, b, t, P.eps_const);
+      const SdfSample sm = sdf_bilinear<IO, false>(sdf + (size_t)b * P.sdf_sb, P.H, P.W, P.orig_x, P.orig_y, P.res, thc[0],
+                                                   thc[1], P.inv_res);
+      const ObsTerm ob = hinge(sm, __dadd_rn(eps, P.r_sphere));
+      const double k = (ge * P.w_fix + go) * ob.c;
+      g[0] -= k * ob.hx;
+      g[1] -= k * ob.hy;
+    }
+    if constexpr (DOF == 3) {
+      if (P.flags & FLAG_NONHOLONOMIC) {       // e = vy cos h - vx sin h (weighted error only)
+        double sh, ch;
+        sincos(thc[2], &sh, &ch);
+        const double e = thc[4] * ch - thc[3] * sh, k = ge * P.kd * e;
+        g[2] += k * (-thc[4] * sh - thc[3] * ch);
+        g[3] += k * (-sh);
+        g[4] += k * ch;
+      }
+    }
+    if constexpr (DOF == 2) {
+      if (P.flags & FLAG_VEL_LIMITS) {          // c = |v| - limit when |v| >= limit
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const double v = thc[2 + q], lim = (q == 0) ? P.vx_lim : P.vy_lim;
+          if (fabs(v) >= lim) g[2 + q] += ge * P.kv * (fabs(v) - lim) * (double)((v > 0.0) - (v < 0.0));
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < D; ++a) g_th[(size_t)i * D + a] = (IO)g[a];
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Information band to HBM in double (inspection / parity).
 // ---------------------------------------------------------------------------
 template <int DOF, typename IO>

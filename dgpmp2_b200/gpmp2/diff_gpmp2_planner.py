@@ -42,20 +42,54 @@ class DiffGPMP2Planner(nn.Module):
         self.non_holonomic = bool(planner_params.get('non_holonomic', False))
         self.use_vel_limits = bool(planner_params.get('use_vel_limits', False))
         self.batch_size = batch_size
+        nl = robot_model.nlinks
+        # module slots with the reference's names (:51-52, :87-88): a reference checkpoint's keys
+        # (learn_module_conv.*, learn_module_fcn.*) line up once modules are assigned to them
         self.learn_module_conv = None
         self.learn_module_fcn = None
-        if learn_params is not None:
-            raise NotImplementedError(
-                'learned-covariance networks (reference diff_gpmp2/learning) are outside the GN hot path this package '
-                'implements; predict the covariances with your own module, map them with get_covariances() and call '
-                'planner.plan_layer(th, start, goal, im, sdf, qc_inv, obscov_inv, eps) directly')
-        nl = robot_model.nlinks
+        self._module_protocol = 'none'
         qc_inv = torch.as_tensor(gp_params['Q_c_inv'])
-        inv_cov = mat_utils.isotropic_matrix(1.0 / torch.pow(torch.as_tensor(obs_params['cost_sigma']), 2.0), nl)
-        # constant per-trajectory covariances, same shapes as the reference (:41-48)
-        self.qc_inv_traj = torch.zeros(self.num_gp_factors, self.dof, self.dof) + qc_inv
-        self.obscov_inv_traj = torch.zeros(self.num_traj_states, nl, 1) + inv_cov
-        self.eps_traj = torch.zeros(self.num_traj_states, nl, 1) + torch.as_tensor(obs_params['epsilon_dist'])
+        if learn_params is None:
+            inv_cov = mat_utils.isotropic_matrix(1.0 / torch.pow(torch.as_tensor(obs_params['cost_sigma']), 2.0), nl)
+            # constant per-trajectory covariances, same shapes as the reference (:41-48)
+            self.qc_inv_traj = torch.zeros(self.num_gp_factors, self.dof, self.dof) + qc_inv
+            self.obscov_inv_traj = torch.zeros(self.num_traj_states, nl, 1) + inv_cov
+            self.eps_traj = torch.zeros(self.num_traj_states, nl, 1) + torch.as_tensor(obs_params['epsilon_dist'])
+        else:
+            # Reference :53-88.  The networks themselves (LearnModuleConv / LearnModuleFCN, reference learning/*) are
+            # outside this package: everything the constructor derives from learn_params is derived here, the two
+            # module slots stay empty until the caller assigns modules with the reference's call protocol
+            # (conv(im_in) -> (features, _); fcn(th_in, features[, hidden]) -> out (B,1,out_dim)[, hidden]), and
+            # step / forward raise until then.  learn_params is updated in place exactly as the reference does.
+            lp = learn_params
+            self.model_type = lp['model']['type'] if 'type' in lp['model'] else False
+            self.learn_eps = lp['dgpmp2']['learn_eps'] if 'learn_eps' in lp['dgpmp2'] else False
+            self.sdf_predict = lp['dgpmp2']['sdf_predict']
+            self.use_dtheta = lp['dgpmp2']['dtheta_predict'] if 'dtheta_predict' in lp['dgpmp2'] else False
+            self.res = (env_params['x_lims'][1] - env_params['x_lims'][0]) / (lp['data']['im_size'] * 1.0)
+            lp['num_traj_states'] = self.num_traj_states
+            lp['state_dim'] = self.state_dim
+            if self.use_dtheta:
+                lp['num_traj_states'] = 2 * self.num_traj_states
+            self.dynamics_mode = lp['dgpmp2']['dynamics_mode']
+            n_obs = self.num_obs_factors * nl
+            if self.dynamics_mode == 'fix_dynamics':
+                lp['out_dim'] = n_obs
+                self.qc_inv_traj = torch.zeros(self.num_gp_factors, self.dof, self.dof) + qc_inv
+            elif self.dynamics_mode == 'diag_identity':
+                lp['out_dim'] = self.num_gp_factors + n_obs
+            elif self.dynamics_mode in ('diag', 'qc_full'):
+                lp['out_dim'] = self.num_gp_factors * self.dof + n_obs
+            elif self.dynamics_mode == 'q_full':
+                lp['out_dim'] = self.num_gp_factors * self.state_dim + n_obs
+            if self.learn_eps:
+                lp['out_dim'] = lp['out_dim'] + n_obs
+            else:
+                self.eps = obs_params['epsilon_dist']
+                self.eps_traj = torch.zeros(self.num_traj_states, nl, 1) + torch.as_tensor(self.eps)
+            self.fixed_conv = lp['dgpmp2']['fixed_conv'] if 'fixed_conv' in lp['dgpmp2'] else False
+            self.out_dim = lp.get('out_dim')
+            self._module_protocol = 'reference'
         self.plan_layer = PlanLayer(gp_params, obs_params, planner_params, optim_params, env_params, robot_model,
                                     learn_params, batch_size, self.use_cuda)
 
@@ -79,7 +113,7 @@ class DiffGPMP2Planner(nn.Module):
         pl._state = dict(start=startb, goal=goalb, qc=qc, w=w, eps=eps, static=True)
         needs_grad = torch.is_grad_enabled() and any(
             isinstance(t, torch.Tensor) and t.requires_grad for t in (th_initb, startb, goalb, sdfb))
-        if self.learn_module_fcn is not None:
+        if self._module_protocol != 'none':
             # covariances re-predicted at every iterate (:128-147): batched step() loop through the fused head
             return self._forward_timed(th_initb, startb, goalb, imb, sdfb, plan_time, start_t, torch.is_grad_enabled())
         if plan_time != float('inf') or needs_grad:
@@ -141,6 +175,28 @@ class DiffGPMP2Planner(nn.Module):
         self.learn_module_fcn = module
         self.dynamics_mode = dynamics_mode
         self.learn_eps = bool(learn_eps)
+        self._module_protocol = 'callable'
+
+    def _predict(self, th_currb, imb, sdfb, conv_out=None, dtheta_currb=None, hiddenb=None):
+        """Run the installed learned module(s) -> (out (B,1,out_dim), hidden).  'reference' protocol (planner built with
+        learn_params; modules assigned to the learn_module_conv / learn_module_fcn slots): the reference's own call
+        sequence (:186-193).  'callable' protocol (set_learn_module): out = module(th, im, sdf)."""
+        if self._module_protocol == 'callable':
+            return self.learn_module_fcn(th_currb, imb, sdfb), None
+        if self.learn_module_fcn is None or (not self.fixed_conv and self.learn_module_conv is None):
+            raise RuntimeError(
+                'DiffGPMP2Planner was built with learn_params but no learned module is installed: assign modules to '
+                'planner.learn_module_conv / planner.learn_module_fcn (the reference\'s LearnModuleConv / LearnModuleFCN '
+                'protocol, out_dim = %s for dynamics_mode %r) or call planner.set_learn_module(module, dynamics_mode). '
+                'The networks themselves are outside this package (reference diff_gpmp2/learning).'
+                % (self.learn_params.get('out_dim'), self.dynamics_mode))
+        if not self.fixed_conv:
+            im_in = torch.cat((imb, sdfb), dim=1) if self.sdf_predict else imb
+            conv_out, _ = self.learn_module_conv(im_in)
+        th_in = torch.cat((th_currb, dtheta_currb), dim=-1) if self.use_dtheta else th_currb
+        if self.model_type == 'feed_forward':
+            return self.learn_module_fcn(th_in, conv_out), None
+        return self.learn_module_fcn(th_in, conv_out, hiddenb)
 
     def step_head(self, th_currb, startb, goalb, imb, sdfb, out, mode=None, learn_eps=None):
         """One batched GN iteration from the learned module's raw output ``out`` (B,1,out_dim):
@@ -153,8 +209,8 @@ class DiffGPMP2Planner(nn.Module):
     def step(self, th_currb, startb, goalb, imb, sdfb, conv_out=None, dtheta_currb=None, hiddenb=None):
         """One batched GN iteration -> (dthetab, hidden, err_oldb, err_ext_oldb, qc_inv, obscov_inv, eps)."""
         B = th_currb.shape[0]
-        if self.learn_module_fcn is not None:
-            out = self.learn_module_fcn(th_currb, imb, sdfb)
+        if self._module_protocol != 'none':
+            out, hidden = self._predict(th_currb, imb, sdfb, conv_out, dtheta_currb, hiddenb)
             dthetab, err_oldb, err_ext_oldb = self.step_head(th_currb, startb, goalb, imb, sdfb, out)
             with torch.no_grad():       # the covariances of the return tuple are reporting only (train_planner.py:310-311)
                 cov = self.get_covariances(out, self.dynamics_mode, self.learn_eps)
@@ -163,7 +219,7 @@ class DiffGPMP2Planner(nn.Module):
                     cov.insert(0, self.qc_inv_traj.to(out.device, out.dtype).unsqueeze(0).expand(B, -1, -1, -1))
                 if not self.learn_eps:
                     cov.append(self.eps_traj.to(out.device, out.dtype).unsqueeze(0).expand(B, -1, -1, -1))
-            return dthetab, None, err_oldb, err_ext_oldb, cov[0], cov[1], cov[2]
+            return dthetab, (hidden if hiddenb is not None else None), err_oldb, err_ext_oldb, cov[0], cov[1], cov[2]
         qc, w, eps = self.plan_layer.static_weights(B, th_currb)
         dthetab, err_oldb, err_ext_oldb = self.plan_layer(th_currb, startb, goalb, imb, sdfb, qc, w, eps)
         return dthetab, None, err_oldb, err_ext_oldb, qc, w, eps

@@ -16,6 +16,7 @@ staged to the GPU and the results handed back on the caller's device.
 """
 import torch
 import torch.nn as nn
+from torch.autograd.function import once_differentiable
 
 from .. import _lib, ops
 from .._dev import as_float, back, to_cuda, work_dtype
@@ -51,6 +52,7 @@ class _GNStep(torch.autograd.Function):
         return out
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_dth, g_err, g_err_ext):
         layer, static, head, dt = ctx.layer, ctx.static, ctx.head, ctx.dt
         saved = ctx.saved_tensors
@@ -80,11 +82,55 @@ class _GNStep(torch.autograd.Function):
                 g_eps = 2.0 * e * g_eps
 
         def fit(g, k):
+            """kernel gradient (dense per (b, t)) -> the input's own shape: broadcast inputs ((1,T-1,dof,dof), (B,1,..),
+            (1,T,1,1): make_weights passes them with stride 0) receive the SUM over the dimensions they were
+            broadcast along, as autograd would give for an expanded tensor."""
             if g is None or ctx.meta[k] is None:
                 return None
             dev, dtype, shape = ctx.meta[k]
+            if k >= 4 and g.numel() != int(torch.Size(shape).numel()) and len(shape) >= 2:
+                full = list(shape)
+                full[0], full[1] = g.shape[0], g.shape[1]      # the kernel's gradient is dense over (problem, factor / state)
+                g = g.reshape(full).sum_to_size(shape)
             return g.reshape(shape).to(device=dev, dtype=dtype)
         return (None, None, None, fit(g_th, 0), fit(g_start, 1), fit(g_goal, 2), fit(g_sdf, 3), fit(g_qc, 4), fit(g_w, 5), fit(g_eps, 6))
+
+
+class _Errors(torch.autograd.Function):
+    """(err, err_ext, err_sg, err_gp, err_obs) of one factor sweep (dgpmp2_errors_*), differentiable w.r.t. the
+    trajectory like the reference's error_ext_batch / gp_error / obs_error / start_goal_error (plan_layer.py:310-388;
+    the training loss of learning/train_planner.py:327-346 is built from them).  err is not differentiable (the
+    reference computes it under no_grad, :275).  Backward: dgpmp2_errors_backward_*."""
+
+    @staticmethod
+    def forward(ctx, layer, th, sdf):
+        s = layer._state
+        dt = work_dtype(th, sdf)
+        p, kw = layer._installed(dt)
+        thc, stc, goc, sdfc = to_cuda(th, dt), to_cuda(s['start'], dt), to_cuda(s['goal'], dt), to_cuda(sdf, dt)
+        outs = ops.errors(p, thc, stc, goc, sdfc, **kw)
+        ctx.layer, ctx.dt, ctx.head = layer, dt, kw.get('head')
+        ctx.meta = (th.device, th.dtype, tuple(th.shape))
+        eps = kw.get('eps')
+        ctx.has_eps = eps is not None
+        ctx.save_for_backward(thc, stc, goc, sdfc, *([eps] if eps is not None else []))
+        res = tuple(back(o, th).to(th.dtype) for o in outs)
+        ctx.mark_non_differentiable(res[0])
+        return res
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_err, g_ext, g_sg, g_gp, g_obs):
+        saved = ctx.saved_tensors
+        thc, stc, goc, sdfc = saved[:4]
+        eps = saved[4] if ctx.has_eps else None
+        if not ctx.needs_input_grad[1]:
+            return None, None, None
+        p = ctx.layer.cparams(q_full=False)
+        c = lambda g: None if g is None else to_cuda(g, ctx.dt).reshape(-1)
+        g_th = ops.errors_backward(p, thc, stc, goc, sdfc, c(g_ext), c(g_sg), c(g_gp), c(g_obs), eps=eps, head=ctx.head)
+        dev, dtype, shape = ctx.meta
+        return None, g_th.reshape(shape).to(device=dev, dtype=dtype), None
 
 
 class PlanLayer(nn.Module):
@@ -247,13 +293,10 @@ class PlanLayer(nn.Module):
         return p, dict(qc_inv=c(s['qc']), w_obs=c(s['w']), eps=c(s['eps']), head=head)
 
     def _errors(self, thb, sdfb):
+        """(err, err_ext, err_sg, err_gp, err_obs), each (B,), differentiable w.r.t. thb (err excepted)."""
         if self._state is None:
             raise RuntimeError('PlanLayer: call forward() (or set the factor means / covariances) before error_batch')
-        s = self._state
-        dt = work_dtype(thb, sdfb)
-        p, kw = self._installed(dt)
-        outs = ops.errors(p, to_cuda(thb, dt), to_cuda(s['start'], dt), to_cuda(s['goal'], dt), to_cuda(sdfb, dt), **kw)
-        return [back(o, thb).to(thb.dtype) for o in outs]
+        return list(_Errors.apply(self, thb, sdfb))
 
     def error_batch(self, thb, sdfb):
         """Normalised weighted error 0.5 sum e^T K e / M with the covariances of the last forward() -> (B,1,1)."""

@@ -10,6 +10,22 @@ from . import _lib
 from ._lib import CParams, check, load, make_weights, ptr, stream_ptr, suffix
 
 
+def _on_tensor_device(fn):
+    """Run the op with the CUDA device of its first CUDA tensor argument current: the C ABI launches on the current
+    device (stream_ptr() hands it that device's current stream, c_abi.cu sizes its launches from cudaGetDevice), so
+    tensors living on cuda:1 while cuda:0 is current would otherwise be launched on the wrong device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def _prep(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     if not t.is_cuda:
         raise _lib.Dgpmp2Error('%s must be a CUDA tensor (no CPU path)' % name)
@@ -41,6 +57,9 @@ def _common(p: CParams, th, start, goal, sdf):
     start = _prep(start, dtype, 'start').reshape(B, d) if start is not None else None
     goal = _prep(goal, dtype, 'goal').reshape(B, d) if goal is not None else None
     sdf, sdf_sb = _sdf3(_prep(sdf, dtype, 'sdf'), B)
+    for name, t in (('start', start), ('goal', goal), ('sdf', sdf)):
+        if t is not None and t.device != th.device:
+            raise ValueError('%s is on %s but th is on %s: all tensors of a call must share one device' % (name, t.device, th.device))
     p.B = B
     _lib.set_sdf_shape(p, sdf.shape[1], sdf.shape[2], sdf_sb)
     return th, start, goal, sdf
@@ -77,6 +96,7 @@ def _prep_w(t, dtype):
     return t if t.dtype == dtype else t.to(dtype)
 
 
+@_on_tensor_device
 def gn_step(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, want_status=True, out=None, head=None):
     """One batched GN iteration. Returns dth (B,T,d), err (B,), err_ext (B,), status (B,) int32 or None.
     `out`: optional preallocated contiguous CUDA tensor (B,T,d) of th's dtype that receives dth.
@@ -99,6 +119,7 @@ def gn_step(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None,
     return dth, err, err_ext, status
 
 
+@_on_tensor_device
 def gn_step_diag(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, head=None):
     """gn_step (float32 I/O) that also reports how the mixed-precision kernel solved each problem:
     returns dth, err, err_ext, status, refine (B,) int32 -- k > 0: accepted after k refinement iterations,
@@ -118,6 +139,7 @@ def gn_step_diag(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=
     return dth, err, err_ext, status, refine
 
 
+@_on_tensor_device
 def gn_step_backward(p: CParams, th, start, goal, sdf, dth, g_dth, g_err_ext=None, qc_inv=None, w_obs=None, eps=None,
                      need_th=True, need_start=False, need_goal=False, need_qc=False, need_w=False, need_eps=False,
                      need_sdf=False, head=None):
@@ -144,6 +166,7 @@ def gn_step_backward(p: CParams, th, start, goal, sdf, dth, g_dth, g_err_ext=Non
     return g_th, g_start, g_goal, g_qc, g_w, g_eps, g_sdf
 
 
+@_on_tensor_device
 def gn_solve(p: CParams, th, start, goal, sdf, max_iters: int, tol_delta: float, qc_inv=None, w_obs=None, eps=None,
              head=None):
     """Persistent solve to convergence. Returns th_final, iters, err_per_iter (B,max_iters; NaN beyond iters),
@@ -165,6 +188,7 @@ def gn_solve(p: CParams, th, start, goal, sdf, max_iters: int, tol_delta: float,
     return th_final, iters, epi, eepi, ef, eef, status
 
 
+@_on_tensor_device
 def errors(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, head=None):
     """Factor sweep. Returns err, err_ext, err_sg, err_gp, err_obs, each (B,)."""
     th, start, goal, sdf = _common(p, th, start, goal, sdf)
@@ -176,6 +200,27 @@ def errors(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, 
     return tuple(outs)
 
 
+@_on_tensor_device
+def errors_backward(p: CParams, th, start, goal, sdf, g_ext=None, g_sg=None, g_gp=None, g_obs=None, eps=None, head=None):
+    """Backward of ``errors`` w.r.t. th: g_* are (B,) upstream gradients of err_ext / err_sg / err_gp / err_obs
+    (None = 0; err has no gradient, as in the reference).  Returns g_th (B,T,d)."""
+    th, start, goal, sdf = _common(p, th, start, goal, sdf)
+    B, T, d = th.shape
+    gs = [None if g is None else _prep(g.reshape(B), th.dtype, 'upstream gradient') for g in (g_ext, g_sg, g_gp, g_obs)]
+    g_th = torch.empty_like(th)
+    wref, keep = None, []
+    if eps is not None and head is not None:        # raw head output: the kernel squares it (DGPMP2_FLAG_HEAD)
+        p.flags |= _lib.FLAG_HEAD
+        w, keep = _lib.make_head_weights(None, None, _prep_w(eps, th.dtype), B, T, 0)
+        wref, keep = ctypes.byref(w), keep + [w]
+    elif eps is not None:
+        wref, keep = _weights(p, th.dtype, None, None, eps, B, T)
+    fn = getattr(load(), 'dgpmp2_errors_backward_' + suffix(th.dtype))
+    check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(sdf), wref, *[ptr(g) for g in gs], ptr(g_th), stream_ptr()))
+    return g_th
+
+
+@_on_tensor_device
 def factors(p: CParams, th, sdf=None, eps=None, want_gp=True, want_obs=True, want_custom=False):
     """Stand-alone factor outputs: gp_err (B,T-1,d), obs_cost (B,T), obs_H (B,T,d), cust_err, cust_H (or None)."""
     _lib.require_cuda()
@@ -203,6 +248,7 @@ def factors(p: CParams, th, sdf=None, eps=None, want_gp=True, want_obs=True, wan
     return gp, oc, oh, ce, ch
 
 
+@_on_tensor_device
 def sdf_lookup(sdf, pts, res: float, x_lo: float, y_lo: float):
     """bilinear_interpolate: sdf (B,H,W), pts (B,N,2) -> dist (B,N,1), J (B,N,2)."""
     _lib.require_cuda()
@@ -218,6 +264,7 @@ def sdf_lookup(sdf, pts, res: float, x_lo: float, y_lo: float):
     return dist, J
 
 
+@_on_tensor_device
 def sdf_from_occupancy(im, padlen: int = 1, res: float = 1.0, thresh: float = 0.75):
     """Batched signed distance field on the GPU: im (B,H,W) or (H,W) CUDA tensor -> (B,H+2p,W+2p), exact EDT."""
     _lib.require_cuda()
@@ -232,6 +279,7 @@ def sdf_from_occupancy(im, padlen: int = 1, res: float = 1.0, thresh: float = 0.
     return out
 
 
+@_on_tensor_device
 def band(p: CParams, th, start, goal, sdf, qc_inv=None, w_obs=None, eps=None, head=None):
     """Information band in float64: D (B,T,d,d), U (B,T-1,d,d), r (B,T,d)."""
     th, start, goal, sdf = _common(p, th, start, goal, sdf)
@@ -267,14 +315,38 @@ class HostStepper:
         self.h2d_bytes = (B * T * d + 2 * B * d) * es
         self.sdf_bytes = (p.H * p.W if p.sdf_stride_b == 0 else p.sdf_stride_b * B) * es
         self.d2h_bytes = (B * T * d + 2 * B) * es + 4 * B
+        self._sdf_staged = False
+
+    def _check_host(self, t, name, numel):
+        if not isinstance(t, torch.Tensor) or t.is_cuda:
+            raise _lib.Dgpmp2Error('HostStepper.step: %s must be a HOST tensor' % name)
+        if t.dtype != self.dtype:
+            raise TypeError('HostStepper.step: %s is %s, the stepper was built for %s' % (name, t.dtype, self.dtype))
+        if not t.is_contiguous():
+            raise ValueError('HostStepper.step: %s must be contiguous' % name)
+        if t.numel() != numel:
+            raise ValueError('HostStepper.step: %s has %d elements, expected %d' % (name, t.numel(), numel))
 
     def step(self, th, start, goal, sdf, sdf_resident=False):
         """Host tensors (contiguous, ideally pinned) -> (dth, err, err_ext, status) pinned host tensors.
-        Synchronous: returns when the results are in host memory."""
+        Synchronous: returns when the results are in host memory.  ``sdf_resident=True`` reuses the SDF a previous
+        call of this stepper copied to the device workspace (``sdf`` may then be None)."""
+        p = self.p
+        B, T, d = p.B, p.T, 2 * p.dof
+        self._check_host(th, 'th', B * T * d)
+        self._check_host(start, 'start', B * d)
+        self._check_host(goal, 'goal', B * d)
+        if sdf_resident:
+            if not self._sdf_staged:
+                raise _lib.Dgpmp2Error('HostStepper.step: sdf_resident=True before any call has staged an SDF')
+        else:
+            self._check_host(sdf, 'sdf', p.H * p.W if p.sdf_stride_b == 0 else p.sdf_stride_b * B)
         fn = getattr(load(), 'dgpmp2_gn_step_host_' + suffix(self.dtype))
-        check(fn(ctypes.byref(self.p), ptr(th), ptr(start), ptr(goal), ptr(sdf), ptr(self.dth), ptr(self.err),
-                 ptr(self.err_ext), ptr(self.status), ctypes.c_void_p(self.ws.data_ptr()), self.ws.numel(),
-                 1 if sdf_resident else 0, stream_ptr()))
+        with torch.cuda.device(self.device):
+            check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(None if sdf_resident else sdf), ptr(self.dth),
+                     ptr(self.err), ptr(self.err_ext), ptr(self.status), ctypes.c_void_p(self.ws.data_ptr()), self.ws.numel(),
+                     1 if sdf_resident else 0, stream_ptr()))
+        self._sdf_staged = True
         return self.dth, self.err, self.err_ext, self.status
 
 

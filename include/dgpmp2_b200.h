@@ -191,6 +191,23 @@ int dgpmp2_errors_f64(const dgpmp2_params* p, const double* th, const double* st
                       double* err, double* err_ext, double* err_sg, double* err_gp, double* err_obs, void* stream);
 
 /*
+ * Backward of dgpmp2_errors_* w.r.t. the trajectory -- replaces autograd through error_ext_batch (:310-345),
+ * start_goal_error / gp_error / obs_error (:374-388), which the reference's training loss is built from
+ * (learning/train_planner.py:327-346: unweighted_errors_batch(th_new) -> gp + sg + lambda * obs, error_ext).
+ *   g_err_ext, g_err_sg, g_err_gp, g_err_obs: (B) upstream gradients, any may be NULL (= 0);
+ *   err has no gradient (the reference computes it under torch.no_grad, :275).
+ *   -> g_th (B,T,d) = sum_k g_err_k[b] * d err_k[b] / d th[b].  Only w->eps is read from the weights (the
+ *   obstacle cost uses the installed eps; err_ext uses the constructor-time covariances).
+ */
+int dgpmp2_errors_backward_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal,
+                               const float* sdf, const dgpmp2_weights* w, const float* g_err_ext, const float* g_err_sg,
+                               const float* g_err_gp, const float* g_err_obs, float* g_th, void* stream);
+int dgpmp2_errors_backward_f64(const dgpmp2_params* p, const double* th, const double* start, const double* goal,
+                               const double* sdf, const dgpmp2_weights* w, const double* g_err_ext,
+                               const double* g_err_sg, const double* g_err_gp, const double* g_err_obs, double* g_th,
+                               void* stream);
+
+/*
  * Stand-alone factor outputs -- replaces GPFactor.get_error (gp_factor.py:100-110),
  * ObstacleFactor.get_error (obstacle_factor.py:35-40) incl.
  * HingeLossObstacleCost.hinge_loss_signed_batch (obstacle_cost.py:29-38),

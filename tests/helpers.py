@@ -73,3 +73,25 @@ def head_oracle_weights(g, p):
     if eps is None:
         eps = torch.full((B, T, 1, 1), p.epsilon_dist, dtype=torch.float64)
     return qc, w, eps, mode == 'q_full'
+
+
+def custom_base(g):
+    """Planner constants a custom_* golden case was generated with (oracle/make_golden_r2.py)."""
+    kv = dict(zip([str(k) for k in g['params_keys']], [str(v) for v in g['params_vals']]))
+    import ast
+    return {k: ast.literal_eval(v) for k, v in kv.items()}
+
+
+def custom_flags(g):
+    f = {}
+    if bool(g['non_holonomic']):
+        f['non_holonomic'] = True
+    if bool(g['use_vel_limits']):
+        f['use_vel_limits'] = True
+    return f
+
+
+def custom_oracle_params(g):
+    base = custom_base(g)
+    extra = {k: base[k] for k in ('K_v', 'v_x', 'v_y') if k in base and bool(g['use_vel_limits'])}
+    return oracle_params(g['T'], g['x_lims'], g['y_lims'], base=base, dof=int(g['dof']), **custom_flags(g), **extra)

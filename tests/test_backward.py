@@ -128,3 +128,79 @@ def test_forward_is_differentiable_like_the_reference_example():
         x = x + gn_oracle.gn_step(x, start, goal, sdf, qc, w, eps, p)[0]
     (x * R).sum().backward()
     _close(th0.grad.numpy(), th.grad.numpy(), 1e-6, 'd th_final / d th_init')
+
+
+def test_oracle_error_gradients_match_reference_autograd():
+    """d(err_ext, err_sg, err_gp, err_obs)/d th of the oracle's restatement vs the LIVE reference's autograd through
+    error_ext_batch / unweighted_errors_batch (tests/golden/errgrad_B2_T16.npz, oracle/make_golden_r2.py)."""
+    g = load_golden('errgrad_B2_T16')
+    assert not bool(g['err_requires_grad'])
+    p = oracle_params(g['T'])
+    th = t64(g['th']).requires_grad_(True)
+    start, goal, sdf, eps = (t64(g[k]) for k in ('start', 'goal', 'sdf', 'eps'))
+    B, T = th.shape[0], int(g['T'])
+    q_fix, w_fix = gn_oracle.fixed_covariances(p, B)
+    e_ext = gn_oracle.weighted_error(th, start, goal, sdf, q_fix, w_fix, eps, p)
+    e_sg, e_gp, e_obs = gn_oracle.unweighted_errors(th, start, goal, sdf, eps, p)
+    for k, e in dict(ext=e_ext, sg=e_sg, gp=e_gp, obs=e_obs).items():
+        np.testing.assert_allclose(e.detach().numpy().reshape(g['err_' + k].shape), g['err_' + k], rtol=1e-12)
+        gr, = torch.autograd.grad((e.reshape(g['c_' + k].shape) * t64(g['c_' + k])).sum(), th, retain_graph=True)
+        _close(gr.numpy(), g['g_th_' + k], 1e-10, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+def test_cuda_error_gradients_match_reference_autograd(dtype):
+    """error_ext_batch / gp_error / obs_error / start_goal_error / unweighted_errors_batch are differentiable w.r.t. the
+    trajectory, as in the reference (its training loss is built from them: learning/train_planner.py:327-346)."""
+    from tests.test_gpu_api import _planner
+    g = load_golden('errgrad_B2_T16')
+    planner = _planner(int(g['T']), 2)
+    pl = planner.plan_layer
+    cast = lambda k: torch.as_tensor(g[k]).to(dtype)
+    with torch.no_grad():
+        pl(cast('th'), cast('start'), cast('goal'), None, cast('sdf'), cast('qc'), cast('w'), cast('eps'))
+    tol = 1e-9 if dtype == torch.float64 else 2e-5
+    for k in ('ext', 'sg', 'gp', 'obs'):
+        leaf = cast('th').requires_grad_(True)
+        if k == 'ext':
+            e = pl.error_ext_batch(leaf, cast('sdf'))
+        else:
+            e = dict(zip(('sg', 'gp', 'obs'), planner.unweighted_errors_batch(leaf, cast('sdf'))))[k]
+        assert e.requires_grad and tuple(e.shape) == g['err_' + k].shape
+        np.testing.assert_allclose(e.detach().double().numpy(), g['err_' + k], rtol=1e-11 if dtype == torch.float64 else 1e-6)
+        (e * torch.as_tensor(g['c_' + k]).to(dtype)).sum().backward()
+        _close(leaf.grad.double().numpy(), g['g_th_' + k], tol, k)
+    leaf = cast('th').requires_grad_(True)
+    assert not pl.error_batch(leaf, cast('sdf')).requires_grad            # computed under no_grad in the reference (:275)
+    # the single-quantity accessors are differentiable too
+    e = pl.gp_error(leaf).sum() + pl.start_goal_error(leaf).sum() + pl.obs_error(leaf, cast('sdf')).sum()
+    e.backward()
+    want = g['g_th_gp'] / g['c_gp'].reshape(-1, 1, 1) + g['g_th_sg'] / g['c_sg'].reshape(-1, 1, 1) + g['g_th_obs'] / g['c_obs'].reshape(-1, 1, 1)
+    _close(leaf.grad.double().numpy(), want, tol * 10, 'sum of accessors')
+
+
+@pytest.mark.gpu
+def test_broadcast_weights_receive_summed_gradients():
+    """Expanded / broadcast-shaped weights ((1,T-1,dof,dof), (1,T,1,1), (B,1,1,1)) are accepted by forward without
+    copies (make_weights, stride 0); backward must hand back their own shape, summed over the broadcast dimensions."""
+    from tests.test_gpu_api import _planner
+    g = load_golden('grad_B2_T16')
+    planner = _planner(int(g['T']), 2)
+    B, T = 2, int(g['T'])
+    th, start, goal, sdf = (t64(g[n]) for n in ('th', 'start', 'goal', 'sdf'))
+    qc1 = t64(g['qc'])[:1].clone().requires_grad_(True)            # (1,T-1,2,2)
+    w1 = t64(g['w'])[:1].clone().requires_grad_(True)              # (1,T,1,1)
+    e1 = t64(g['eps'])[:, :1].clone().requires_grad_(True)         # (B,1,1,1)
+    dth, _, err_ext = planner.plan_layer(th, start, goal, None, sdf, qc1, w1, e1)
+    loss = (dth * t64(g['G'])).sum() + (err_ext * t64(g['g_err_ext'])).sum()
+    loss.backward()
+    qcf = qc1.detach().expand(B, -1, -1, -1).clone().requires_grad_(True)
+    wf = w1.detach().expand(B, -1, -1, -1).clone().requires_grad_(True)
+    ef = e1.detach().expand(-1, T, -1, -1).clone().requires_grad_(True)
+    dth2, _, err_ext2 = planner.plan_layer(th, start, goal, None, sdf, qcf, wf, ef)
+    ((dth2 * t64(g['G'])).sum() + (err_ext2 * t64(g['g_err_ext'])).sum()).backward()
+    assert qc1.grad.shape == qc1.shape and w1.grad.shape == w1.shape and e1.grad.shape == e1.shape
+    _close(qc1.grad.numpy(), qcf.grad.sum(0, keepdim=True).numpy(), 1e-12, 'qc')
+    _close(w1.grad.numpy(), wf.grad.sum(0, keepdim=True).numpy(), 1e-12, 'w')
+    _close(e1.grad.numpy(), ef.grad.sum(1, keepdim=True).numpy(), 1e-12, 'eps')

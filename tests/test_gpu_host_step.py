@@ -1,0 +1,103 @@
+"""-m gpu: the end-to-end entry points dgpmp2_gn_step_host_f32 / _f64 (HOST buffers in, HOST buffers out; what
+bench.py's `e2e` number and the planner's CPU-tensor path run through) against the live reference's goldens, with the
+tolerances of tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_golden, rel_err, step_cases
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float64: dict(dth=1e-9, err=1e-11), torch.float32: dict(dth=1e-5, err=1e-6)}
+STATIC = [n for n in step_cases() if bool(load_golden(n)['static'])]
+
+
+def _host(a, dtype, pinned):
+    t = torch.as_tensor(np.ascontiguousarray(a)).to(dtype).contiguous()
+    return t.pin_memory() if pinned else t
+
+
+def _stepper(g, dtype, shared_sdf=False):
+    from dgpmp2_b200 import _lib, ops
+    from tests.gpu_helpers import cparams
+    B, T, d = g['th'].shape
+    H, W = g['sdf'].shape[-2:]
+    cp = cparams(T, B=B, H=H, W=W, x_lims=g['x_lims'], y_lims=g['y_lims'])
+    _lib.set_sdf_shape(cp, H, W, 0 if shared_sdf else H * W)
+    return ops.HostStepper(cp, dtype)
+
+
+def _check(out, g, dtype, rows=slice(None)):
+    dth, err, err_ext, status = out
+    tol = TOL[dtype]
+    assert int(status.abs().max()) == 0
+    assert rel_err(dth[rows], g['dth'][rows]) < tol['dth']
+    np.testing.assert_allclose(err.double().numpy()[rows], g['err'].reshape(-1)[rows], rtol=tol['err'])
+    np.testing.assert_allclose(err_ext.double().numpy()[rows], g['err_ext'].reshape(-1)[rows], rtol=tol['err'])
+
+
+@pytest.mark.parametrize('pinned', [True, False], ids=['pinned', 'pageable'])
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+@pytest.mark.parametrize('name', STATIC)
+def test_host_step_vs_reference_golden(name, dtype, pinned):
+    g = load_golden(name)
+    B, T, d = g['th'].shape
+    hs = _stepper(g, dtype)
+    th, start, goal, sdf = (_host(g[k], dtype, pinned) for k in ('th', 'start', 'goal', 'sdf'))
+    out = hs.step(th, start.reshape(B, d), goal.reshape(B, d), sdf.reshape(B, *g['sdf'].shape[-2:]))
+    assert all(not t.is_cuda for t in out)
+    _check(out, g, dtype)
+    first = [t.clone() for t in out]
+    # the SDF stays in the device workspace: a second call may skip the 4*B*H*W-byte copy and must give the same bits
+    out2 = hs.step(th, start.reshape(B, d), goal.reshape(B, d), None, sdf_resident=True)
+    for a, b in zip(first, out2):
+        assert torch.equal(a, b)
+    # ... also for a different trajectory against the same resident SDF: equal to the device-resident entry point
+    from dgpmp2_b200 import ops
+    from tests.gpu_helpers import cparams
+    th2 = (th + 0.01).contiguous()
+    out3 = [t.clone() for t in hs.step(th2, start.reshape(B, d), goal.reshape(B, d), None, sdf_resident=True)]
+    cp = cparams(T, x_lims=g['x_lims'], y_lims=g['y_lims'])
+    ref = ops.gn_step(cp, th2.cuda(), start.cuda(), goal.cuda(), sdf.cuda())
+    for a, b in zip(out3, ref):
+        assert torch.equal(a, b.cpu())
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+def test_host_step_shared_sdf_stride_zero(dtype):
+    """sdf_stride_b = 0: ONE SDF for the whole batch (H*W elements cross the bus instead of B*H*W)."""
+    g = load_golden('step_static_B4_T64_k0')
+    B, T, d = g['th'].shape
+    hs = _stepper(g, dtype, shared_sdf=True)
+    assert hs.sdf_bytes == g['sdf'].shape[-1] * g['sdf'].shape[-2] * (4 if dtype == torch.float32 else 8)
+    th, start, goal = (_host(g[k], dtype, True) for k in ('th', 'start', 'goal'))
+    sdf0 = _host(g['sdf'][0, 0], dtype, True)
+    out = hs.step(th, start.reshape(B, d), goal.reshape(B, d), sdf0)
+    _check(out, g, dtype, rows=slice(0, 1))          # problem 0 sees its own SDF -> the reference's numbers
+    from dgpmp2_b200 import ops
+    from tests.gpu_helpers import cparams
+    cp = cparams(T, x_lims=g['x_lims'], y_lims=g['y_lims'])
+    ref = ops.gn_step(cp, th.cuda(), start.cuda(), goal.cuda(), sdf0.cuda().reshape(1, 1, *sdf0.shape))
+    for a, b in zip(out, ref):
+        assert torch.equal(a, b.cpu())
+
+
+def test_host_step_validates_its_arguments():
+    from dgpmp2_b200 import _lib
+    g = load_golden('step_static_B2_T3')
+    B, T, d = g['th'].shape
+    hs = _stepper(g, torch.float32)
+    th, start, goal, sdf = (_host(g[k], torch.float32, False) for k in ('th', 'start', 'goal', 'sdf'))
+    start, goal = start.reshape(B, d), goal.reshape(B, d)
+    with pytest.raises(_lib.Dgpmp2Error):
+        hs.step(th, start, goal, None, sdf_resident=True)          # nothing staged yet
+    with pytest.raises(TypeError):
+        hs.step(th.double(), start, goal, sdf)
+    with pytest.raises(ValueError):
+        hs.step(th[:, :, :2], start, goal, sdf)                    # not contiguous / wrong size
+    with pytest.raises(ValueError):
+        hs.step(th, start, goal, sdf[:1])
+    with pytest.raises(_lib.Dgpmp2Error):
+        hs.step(th.cuda(), start, goal, sdf)
+    hs.step(th, start, goal, sdf)

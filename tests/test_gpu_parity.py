@@ -168,3 +168,35 @@ def test_gn_step_output_pointer_alignment_does_not_matter(dof, T):
         got = ops.gn_step(cp, th, start, goal, sdf, out=out)
         assert got[0].data_ptr() == buf.data_ptr() + 4 * off
         assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+@pytest.mark.parametrize('name', ['custom_nonholonomic_B2_T12', 'custom_nonholonomic_B3_T96', 'custom_vel_limits_B3_T64'])
+def test_custom_factor_configs_vs_executed_reference(name, dtype):
+    """BASELINE configs 4 and 5 against fixtures produced by EXECUTING the live reference's masks, factor objects,
+    construct_linear_system_batch, solve_linear_system_batch and error_batch (oracle/make_golden_r2.py; shape-adapter
+    shims only).  cond(Lambda) is 1e5 .. 3e6 here (reg = 0 for config 4), hence 1e-8 rather than 1e-9 for float64."""
+    from dgpmp2_b200 import ops
+    from tests.gpu_helpers import cparams, dev
+    from tests.helpers import custom_base, custom_flags
+    g = load_golden(name)
+    base, flags, dof = custom_base(g), custom_flags(g), int(g['dof'])
+    cp = cparams(g['T'], x_lims=g['x_lims'], y_lims=g['y_lims'], base=base, dof=dof, **flags)
+    th, start, goal, sdf = (dev(g[k], dtype) for k in ('th', 'start', 'goal', 'sdf'))
+    dth, err, err_ext, status = ops.gn_step(cp, th, start, goal, sdf)
+    assert int(status.abs().max()) == 0
+    assert rel_err(dth.cpu(), g['dth']) < (1e-8 if dtype == torch.float64 else 1e-5)
+    rt = TOL[dtype]['err']
+    np.testing.assert_allclose(err.cpu().double().numpy(), g['err'].reshape(-1), rtol=rt)
+    np.testing.assert_allclose(err_ext.cpu().double().numpy(), g['err_ext'].reshape(-1), rtol=rt)
+    D, U, r = ops.band(cp, th, start, goal, sdf)
+    scale = np.abs(g['band_D']).max()
+    assert np.abs(D.cpu().numpy() - g['band_D']).max() < 1e-11 * scale
+    assert np.abs(U.cpu().numpy() - g['band_U']).max() < 1e-11 * scale
+    assert np.abs(r.cpu().numpy() - g['band_r']).max() < 1e-11 * max(1.0, np.abs(g['band_r']).max())
+    _, _, _, ce, ch = ops.factors(cp, th, sdf, want_gp=False, want_obs=False, want_custom=True)
+    tol = 1e-13 if dtype == torch.float64 else 2e-6
+    np.testing.assert_allclose(ce.cpu().double().numpy().reshape(g['cust_err'].shape), g['cust_err'], rtol=0, atol=tol)
+    np.testing.assert_allclose(ch.cpu().double().numpy().reshape(g['cust_H'].shape), g['cust_H'], rtol=tol, atol=tol)
+    e2 = ops.errors(cp, th, start, goal, sdf)
+    np.testing.assert_allclose(e2[0].cpu().double().numpy(), g['err'].reshape(-1), rtol=rt)
