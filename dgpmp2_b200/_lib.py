@@ -73,8 +73,14 @@ PROTOTYPES = {
     'dgpmp2_factors_f64': [_P(CParams), _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp, _vp, _vp],
     'dgpmp2_sdf_lookup_f32': [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _f64, _f64, _f64, _vp, _vp, _vp],
     'dgpmp2_sdf_lookup_f64': [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _f64, _f64, _f64, _vp, _vp, _vp],
+    'dgpmp2_hinge_batch_f32': [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _f64, _f64, _f64, _vp, _i64, _i64, _f64, _f64, _vp, _vp, _vp],
+    'dgpmp2_hinge_batch_f64': [_vp, _i32, _i32, _i32, _i64, _vp, _i32, _f64, _f64, _f64, _vp, _i64, _i64, _f64, _f64, _vp, _vp, _vp],
     'dgpmp2_sdf_from_occupancy_f32': [_vp, _i32, _i32, _i32, _i32, _f64, _f64, _vp, _vp],
     'dgpmp2_sdf_from_occupancy_f64': [_vp, _i32, _i32, _i32, _i32, _f64, _f64, _vp, _vp],
+    'dgpmp2_sdf_from_occupancy_u8_f32': [_vp, _i32, _i32, _i32, _i32, _f64, _f64, _vp, _vp],
+    'dgpmp2_sdf_from_occupancy_bits_f32': [_vp, _i32, _i32, _i32, _f64, _vp, _vp],
+    'dgpmp2_host_step_occ_workspace_bytes': [_P(CParams), _P(_sz)],
+    'dgpmp2_gn_step_host_occ_f32': [_P(CParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     'dgpmp2_band_f32': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp],
     'dgpmp2_band_f64': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp],
     'dgpmp2_host_step_workspace_bytes': [_P(CParams), _i32, _P(_sz)],

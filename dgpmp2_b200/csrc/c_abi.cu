@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -413,18 +414,42 @@ int sdf_lookup_impl(const IO* sdf, int32_t B, int32_t H, int32_t W, int64_t sdf_
 }
 
 template <typename IO>
-int sdf_from_occupancy_impl(const IO* im, int32_t B, int32_t H, int32_t W, int32_t pad, double thresh, double res, IO* out,
+int hinge_batch_impl(const IO* sdf, int32_t B, int32_t H, int32_t W, int64_t sdf_sb, const IO* pts, int32_t N, double res,
+                     double x_lo, double y_lo, const IO* eps, int64_t eps_sb, int64_t eps_sn, double eps_const,
+                     double r_sphere, IO* cost, IO* He, void* stream) {
+  if (B < 0 || N < 0 || H < 1 || W < 1 || !(res > 0.0) || sdf_sb < 0) return DGPMP2_ERR_ARG;
+  if (B == 0 || N == 0) return DGPMP2_OK;
+  if (!sdf || !pts || !cost || !He) return DGPMP2_ERR_ARG;
+  if (reinterpret_cast<unsigned long long>(pts) & (2 * sizeof(IO) - 1)) return DGPMP2_ERR_ARG;   // (x, y) pairs are loaded as one vector
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const double ox = 0.0 - x_lo / res, oy = 0.0 - y_lo / res;
+  const long long n = (long long)B * N;
+  const long long blocks = (n + 511) / 512;
+  if (blocks > 0x7fffffffLL) return DGPMP2_ERR_UNSUPPORTED;
+  hinge_kernel<IO><<<(unsigned)blocks, 256, 0, st>>>(sdf, B, H, W, sdf_sb, pts, N, res, 1.0 / res, ox, oy, eps, eps_sb, eps_sn,
+                                                     eps_const, r_sphere, cost, He);
+  CUDA_TRY(cudaGetLastError());
+  return DGPMP2_OK;
+}
+
+template <typename IN, typename IO>
+int sdf_from_occupancy_impl(const IN* im, int32_t B, int32_t H, int32_t W, int32_t pad, double thresh, double res, IO* out,
                             void* stream) {
   if (B < 0 || H < 1 || W < 1 || pad < 0 || !(res > 0.0)) return DGPMP2_ERR_ARG;
   if (B == 0) return DGPMP2_OK;
   if (!im || !out) return DGPMP2_ERR_ARG;
   const size_t Hp = (size_t)H + 2 * pad, Wp = (size_t)W + 2 * pad;
-  const size_t bytes = Hp * Wp * 2 * sizeof(unsigned short);
-  if (bytes > (size_t)kSmemLimit || Hp >= 65535 || Wp >= 65535) return DGPMP2_ERR_UNSUPPORTED;
-  auto kern = sdf_from_occupancy_kernel<IO>;
+  if (Hp > 254 || Wp > 254) return DGPMP2_ERR_UNSUPPORTED;          // one-byte row distances, 255 = none
+  if (!std::is_arithmetic<IN>::value && pad != 0) return DGPMP2_ERR_UNSUPPORTED;   // bit-packed maps: padlen 0 only
+  // one thread per (column, polarity) envelope: 256 threads when their stacks fit beside the row distances, else fewer
+  int threads = 256;
+  while (threads > 32 && EdtSmem::bytes((int)Hp, (int)Wp, threads) > (size_t)kSmemLimit) threads >>= 1;
+  const size_t bytes = EdtSmem::bytes((int)Hp, (int)Wp, threads);
+  if (bytes > (size_t)kSmemLimit) return DGPMP2_ERR_UNSUPPORTED;
+  auto kern = sdf_from_occupancy_kernel<IN, IO>;
   int rc = allow_smem(kern, (int)bytes);
   if (rc != DGPMP2_OK) return rc;
-  kern<<<B, 256, bytes, static_cast<cudaStream_t>(stream)>>>(im, H, W, pad, thresh, res, out);
+  kern<<<B, threads, bytes, static_cast<cudaStream_t>(stream)>>>(im, H, W, pad, thresh, res, out);
   CUDA_TRY(cudaGetLastError());
   return DGPMP2_OK;
 }
@@ -477,6 +502,45 @@ int gn_step_host_impl(const dgpmp2_params* p, const IO* th, const IO* start, con
   CUDA_TRY(cudaMemcpyAsync(dth, ws + L.dth, B * T * d * sizeof(IO), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(err, ws + L.err, B * sizeof(IO), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(err_ext, ws + L.err_ext, B * sizeof(IO), cudaMemcpyDeviceToHost, st));
+  if (status) CUDA_TRY(cudaMemcpyAsync(status, ws + L.status, B * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return DGPMP2_OK;
+}
+
+
+// End to end from bit-packed occupancy maps: H2D of the trajectories and of B*H*ceil(W/32) words of map bits (1/32 of
+// the float SDF), exact EDT on the device into the workspace's SDF region, GN step, D2H of the results.
+size_t occ_words(const dgpmp2_params* p) { return (size_t)p->B * p->H * ((size_t)(p->W + 31) / 32); }
+
+int gn_step_host_occ_impl(const dgpmp2_params* p, const float* th, const float* start, const float* goal,
+                          const uint32_t* occ_bits, float* dth, float* err, float* err_ext, int32_t* status, void* dev_ws,
+                          size_t dev_ws_bytes, void* stream) {
+  int rc = check_params(p, nullptr);
+  if (rc != DGPMP2_OK) return rc;
+  if (p->B == 0) return DGPMP2_OK;
+  if (!th || !start || !goal || !occ_bits || !dth || !err || !err_ext || !dev_ws) return DGPMP2_ERR_ARG;
+  if (p->sdf_stride_b != (int64_t)p->H * p->W) return DGPMP2_ERR_ARG;          // one map per problem
+  const HostWs L = host_ws_layout(p, sizeof(float));
+  const size_t bits_bytes = occ_words(p) * 4;
+  if (dev_ws_bytes < L.total + align256(bits_bytes)) return DGPMP2_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned char* ws = static_cast<unsigned char*>(dev_ws);
+  const size_t B = p->B, T = p->T, d = 2 * p->dof;
+  CUDA_TRY(cudaMemcpyAsync(ws + L.total, occ_bits, bits_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ws + L.th, th, B * T * d * sizeof(float), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ws + L.start, start, B * d * sizeof(float), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ws + L.goal, goal, B * d * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = sdf_from_occupancy_impl<OccBits, float>(reinterpret_cast<const OccBits*>(ws + L.total), p->B, p->H, p->W, 0, 0.0, p->res,
+                                               reinterpret_cast<float*>(ws + L.sdf), stream);
+  if (rc != DGPMP2_OK) return rc;
+  rc = gn_step_impl<float>(p, reinterpret_cast<float*>(ws + L.th), reinterpret_cast<float*>(ws + L.start),
+                           reinterpret_cast<float*>(ws + L.goal), reinterpret_cast<float*>(ws + L.sdf), nullptr,
+                           reinterpret_cast<float*>(ws + L.dth), reinterpret_cast<float*>(ws + L.err),
+                           reinterpret_cast<float*>(ws + L.err_ext), reinterpret_cast<int32_t*>(ws + L.status), stream);
+  if (rc != DGPMP2_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(dth, ws + L.dth, B * T * d * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(err, ws + L.err, B * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(err_ext, ws + L.err_ext, B * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (status) CUDA_TRY(cudaMemcpyAsync(status, ws + L.status, B * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return DGPMP2_OK;
@@ -602,13 +666,47 @@ int dgpmp2_sdf_lookup_f64(const double* sdf, int32_t B, int32_t H, int32_t W, in
   return sdf_lookup_impl<double>(sdf, B, H, W, sdf_stride_b, pts, N, res, x_lo, y_lo, dist, J, stream);
 }
 
+int dgpmp2_hinge_batch_f32(const float* sdf, int32_t B, int32_t H, int32_t W, int64_t sdf_stride_b, const float* pts,
+                           int32_t N, double res, double x_lo, double y_lo, const float* eps, int64_t eps_stride_b,
+                           int64_t eps_stride_n, double eps_const, double r_sphere, float* cost, float* He, void* stream) {
+  return hinge_batch_impl<float>(sdf, B, H, W, sdf_stride_b, pts, N, res, x_lo, y_lo, eps, eps_stride_b, eps_stride_n,
+                                 eps_const, r_sphere, cost, He, stream);
+}
+int dgpmp2_hinge_batch_f64(const double* sdf, int32_t B, int32_t H, int32_t W, int64_t sdf_stride_b, const double* pts,
+                           int32_t N, double res, double x_lo, double y_lo, const double* eps, int64_t eps_stride_b,
+                           int64_t eps_stride_n, double eps_const, double r_sphere, double* cost, double* He, void* stream) {
+  return hinge_batch_impl<double>(sdf, B, H, W, sdf_stride_b, pts, N, res, x_lo, y_lo, eps, eps_stride_b, eps_stride_n,
+                                  eps_const, r_sphere, cost, He, stream);
+}
+
 int dgpmp2_sdf_from_occupancy_f32(const float* im, int32_t B, int32_t H, int32_t W, int32_t padlen, double thresh,
                                   double res, float* sdf_out, void* stream) {
-  return sdf_from_occupancy_impl<float>(im, B, H, W, padlen, thresh, res, sdf_out, stream);
+  return sdf_from_occupancy_impl<float, float>(im, B, H, W, padlen, thresh, res, sdf_out, stream);
 }
 int dgpmp2_sdf_from_occupancy_f64(const double* im, int32_t B, int32_t H, int32_t W, int32_t padlen, double thresh,
                                   double res, double* sdf_out, void* stream) {
-  return sdf_from_occupancy_impl<double>(im, B, H, W, padlen, thresh, res, sdf_out, stream);
+  return sdf_from_occupancy_impl<double, double>(im, B, H, W, padlen, thresh, res, sdf_out, stream);
+}
+int dgpmp2_sdf_from_occupancy_u8_f32(const uint8_t* im, int32_t B, int32_t H, int32_t W, int32_t padlen, double thresh,
+                                     double res, float* sdf_out, void* stream) {
+  return sdf_from_occupancy_impl<uint8_t, float>(im, B, H, W, padlen, thresh, res, sdf_out, stream);
+}
+
+int dgpmp2_sdf_from_occupancy_bits_f32(const uint32_t* im_bits, int32_t B, int32_t H, int32_t W, double res, float* sdf_out,
+                                       void* stream) {
+  return sdf_from_occupancy_impl<OccBits, float>(reinterpret_cast<const OccBits*>(im_bits), B, H, W, 0, 0.0, res, sdf_out, stream);
+}
+int dgpmp2_host_step_occ_workspace_bytes(const dgpmp2_params* p, size_t* bytes) {
+  if (p == nullptr || bytes == nullptr) return DGPMP2_ERR_ARG;
+  int rc = check_params(p, nullptr);
+  if (rc != DGPMP2_OK) return rc;
+  *bytes = host_ws_layout(p, sizeof(float)).total + align256(occ_words(p) * 4);
+  return DGPMP2_OK;
+}
+int dgpmp2_gn_step_host_occ_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal,
+                                const uint32_t* occ_bits, float* dth, float* err, float* err_ext, int32_t* status,
+                                void* dev_ws, size_t dev_ws_bytes, void* stream) {
+  return gn_step_host_occ_impl(p, th, start, goal, occ_bits, dth, err, err_ext, status, dev_ws, dev_ws_bytes, stream);
 }
 
 int dgpmp2_band_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal, const float* sdf,

@@ -65,6 +65,7 @@ inline KParams make_kparams(const dgpmp2_params* p) {
     }
   k.static_gp = 0;   // set by the caller once the weights are known
   k.ext_same = 0;
+  k.prefetch = (env_int("DGPMP2_PREFETCH", 1) == 1) ? 1 : 0;      // DGPMP2_PREFETCH=2 disables the SDF prefetch (A/B)
   k.mp_accept = ldexpf(1.0f, -env_int("DGPMP2_MP_ACCEPT_LOG2", 17));
   bcr_make_plan(p->T, env_int("DGPMP2_TAIL", kTailMaxDefault), env_int("DGPMP2_WIDE", kWideMinDefault), k.plan);
   return k;

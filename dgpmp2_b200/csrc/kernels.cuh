@@ -10,6 +10,7 @@
 //   factors_kernel    stand-alone factor outputs (GPFactor / ObstacleFactor / custom factors).
 //   sdf_lookup_kernel bilinear_interpolate.
 #pragma once
+#include <type_traits>
 #ifdef DGPMP2_TIMING
 #define DGPMP2_BCR_STAMP(i) do { if (blockIdx.x == (DGPMP2_TIMING - 1) && threadIdx.x == 0) dgpmp2::g_phase_clock_fwd(i); } while (0)
 namespace dgpmp2 { __device__ void g_phase_clock_fwd(int i); }
@@ -80,6 +81,18 @@ __device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO
       thc[a] = (double)tp[a];
       thp[a] = (t > 0) ? (double)tp[a - D] : 0.0;
       thn[a] = (t < T - 1) ? (double)tp[a + D] : 0.0;
+    }
+    if (P.prefetch) {
+      // L2 prefetch of the two SDF rows this state's obstacle factor gathers from, issued before the prior / GP arithmetic
+      // so that the DRAM latency of the (DRAM-cold) gather hides behind it.  A hint only: the pixel is located in float
+      // arithmetic (the exact, branch-deciding location is computed in double inside assemble_node); no register is
+      // held across the arithmetic, unlike an early load.
+      const float fx = (float)P.orig_x + (float)thc[0] * (float)P.inv_res;
+      const float fy = (float)P.orig_y - (float)thc[1] * (float)P.inv_res;
+      const int ix = min(max(__float2int_rd(fx), 0), P.W - 1), iy = min(max(__float2int_rd(fy), 0), P.H - 1);
+      const IO* q = sdf + (size_t)b * P.sdf_sb + (size_t)iy * P.W + ix;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q + ((iy + 1 < P.H) ? P.W : 0)));
     }
     NodeOut<DOF> o;
     assemble_node<DOF, IO>(P, Wt, b, t, thp, thc, thn, start + (size_t)b * D, goal + (size_t)b * D,
@@ -862,6 +875,52 @@ obstacle_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
 }
 
 // ---------------------------------------------------------------------------
+// HingeLossObstacleCost.hinge_loss_signed_batch (obstacle_cost.py:29-38): sphere centres in, hinge cost and its 2-wide
+// gradient out -- the fused SDF bilinear lookup + obstacle cost + Jacobian in its leanest form: per point 8 B of
+// position, four 4-byte taps, 4 + 8 B of output = the 36 algorithmic bytes of SURVEY 8(d).  Two consecutive points per
+// thread: one 16-byte load of both positions, one 8-byte store of both costs, one 16-byte store of both gradients
+// (fp32 I/O), eight independent tap loads in flight.  HBM-bound; what it can reach is set by the 32-byte DRAM sector:
+// a 2 x 2 tap patch touches 2 rows x (1..2) sectors, shared with the neighbouring states of the same trajectory only.
+// ---------------------------------------------------------------------------
+template <typename IO>
+__global__ void __launch_bounds__(256)
+hinge_kernel(const IO* __restrict__ sdf, int B, int H, int W, long long sdf_sb, const IO* __restrict__ pts, int N,
+             double res, double inv_res, double orig_x, double orig_y, const IO* __restrict__ eps, long long e_sb,
+             long long e_sn, double eps_const, double r_sphere, IO* __restrict__ cost, IO* __restrict__ He) {
+  using V2 = typename Vec2<IO>::type;
+  const long long n = (long long)B * N;
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i0 >= n) return;
+  const bool two = (i0 + 1 < n);
+  V2 p[2];
+  p[0] = __ldg(reinterpret_cast<const V2*>(pts) + i0);
+  p[1] = two ? __ldg(reinterpret_cast<const V2*>(pts) + i0 + 1) : p[0];
+  ObsTerm ob[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const long long i = i0 + (two ? k : 0);
+    const int b = (int)(i / N), j = (int)(i - (long long)b * N);
+    const double e = (eps != nullptr) ? ldg_d(eps + (long long)b * e_sb + (long long)j * e_sn) : eps_const;
+    const SdfSample sm = sdf_bilinear<IO, false>(sdf + (size_t)b * sdf_sb, H, W, orig_x, orig_y, res, (double)p[k].x,
+                                                 (double)p[k].y, inv_res);
+    ob[k] = hinge(sm, __dadd_rn(e, r_sphere));
+  }
+  if (two && ((reinterpret_cast<unsigned long long>(cost) | (reinterpret_cast<unsigned long long>(He) >> 1)) & (2 * sizeof(IO) - 1)) == 0) {
+    V2 c; c.x = (IO)ob[0].c; c.y = (IO)ob[1].c;
+    *reinterpret_cast<V2*>(cost + i0) = c;                 // i0 is even: 2-element aligned when the base is
+    V2 h0, h1; h0.x = (IO)ob[0].hx; h0.y = (IO)ob[0].hy; h1.x = (IO)ob[1].hx; h1.y = (IO)ob[1].hy;
+    reinterpret_cast<V2*>(He)[i0] = h0;
+    reinterpret_cast<V2*>(He)[i0 + 1] = h1;
+  } else {
+    for (int k = 0; k < (two ? 2 : 1); ++k) {
+      cost[i0 + k] = (IO)ob[k].c;
+      He[2 * (i0 + k)] = (IO)ob[k].hx;
+      He[2 * (i0 + k) + 1] = (IO)ob[k].hy;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // bilinear_interpolate (utils/sdf_utils.py:38-107)
 // ---------------------------------------------------------------------------
 template <typename IO>
@@ -880,71 +939,187 @@ sdf_lookup_kernel(const IO* __restrict__ sdf, int B, int H, int W, long long sdf
 
 // ---------------------------------------------------------------------------
 // Signed Euclidean distance field of an occupancy image -- replaces sdf_2d (utils/sdf_utils.py:6-21,
-// datasets/utils.py:4-18), i.e. two scipy.ndimage.distance_transform_edt calls per map.
-// One CTA per image.  Pass 1: per column, distance to the nearest background pixel of that column
-// (both polarities at once).  Pass 2: per pixel, exact minimum over the row of dx^2 + g^2 in integer
-// arithmetic (one polarity per pixel, scanned outwards with an exact cut-off), then sqrt in double:
-// bit-identical to the exact EDT.  scipy's behaviour for an image
-// WITHOUT any background pixel (distance to a virtual pixel at row -1, column 0) is reproduced.
+// datasets/utils.py:4-18), i.e. two scipy.ndimage.distance_transform_edt calls per map.  Exact EDT, separable:
+//   A. one warp per image row: the row's free / obstacle pixels as bit masks (__ballot_sync over coalesced loads);
+//   B. per pixel and polarity, the distance ALONG THE ROW to the nearest pixel of that polarity: nearest set bit of the
+//      row mask to the left / right (shift + ffs / clz, no scan) -> one byte per pixel and polarity (255 = none);
+//   C. per column and polarity (one thread each), the exact lower envelope of the parabolas (y - i)^2 + g(i, x)^2 by the
+//      integer stack algorithm of Meijster et al. (a forward sweep that builds the envelope, a backward sweep that
+//      evaluates it; O(H) per column whatever the distances are) -- the backward sweep runs over the rows in lock step,
+//      so the lanes of a warp write consecutive pixels of one row; sqrt in double.
+// A pixel is background of one of the two transforms (distance 0 there), so each pixel needs ONE polarity: free pixels
+// look for the nearest obstacle, obstacle pixels for the nearest free pixel.  Bit-identical to the scipy path, including
+// scipy's behaviour for an image WITHOUT any background pixel (distance to a virtual pixel at row -1, column 0).
+// One CTA per image; 2 bytes + 2 mask bits of shared memory per pixel, so several images are resident per SM.
 // ---------------------------------------------------------------------------
-template <typename IO>
+__device__ __forceinline__ int edt_nearest_bit(const unsigned* __restrict__ m, int NW, int x) {
+  const int w = x >> 5, bp = x & 31;
+  int dr = 255, dl = 255;
+  unsigned v = m[w] >> bp;                                   // bits at positions >= x
+  if (v != 0u) {
+    dr = __ffs(v) - 1;
+  } else {
+    for (int q = w + 1; q < NW; ++q) {
+      const unsigned u = m[q];
+      if (u != 0u) { dr = (q << 5) + __ffs(u) - 1 - x; break; }
+    }
+  }
+  v = m[w] << (31 - bp);                                     // bits at positions <= x, the bit at x in the msb
+  if (v != 0u) {
+    dl = __clz(v);
+  } else {
+    for (int q = w - 1; q >= 0; --q) {
+      const unsigned u = m[q];
+      if (u != 0u) { dl = x - ((q << 5) + 31 - __clz(u)); break; }
+    }
+  }
+  return min(min(dl, dr), 255);
+}
+
+// bit-packed occupancy input: row-major, every row padded to 32-bit words, bit (x & 31) of word x >> 5 set = pixel FREE
+struct OccBits { unsigned w; };
+
+struct EdtSmem {
+  unsigned* m_obst;      // [Hp][NW] bit x of row y: pixel (y, x) is an obstacle
+  unsigned* m_free;      // [Hp][NW] ... is free
+  unsigned char* g0;     // [Hp*Wp] distance along the row to the nearest OBSTACLE pixel (255: none in this row)
+  unsigned char* g1;     // [Hp*Wp] ... to the nearest FREE pixel
+  unsigned char* st_s;   // [Hp][threads] envelope stacks, entry k of the thread's task at [k * threads + tid]: parabola index (row)
+  unsigned char* st_t;   // [Hp][threads] ... first row at which that parabola is the lowest
+  __host__ __device__ static size_t bytes(int Hp, int Wp, int threads) {
+    const size_t NW = (size_t)(Wp + 31) / 32;
+    const size_t stacks = 2 * (size_t)Hp * threads, tmp = (size_t)Hp * Wp;      // (the stacks' area first holds one byte per pixel)
+    return 2 * (size_t)Hp * NW * 4 + 2 * (((size_t)Hp * Wp + 15) & ~(size_t)15) + (stacks > tmp ? stacks : tmp);
+  }
+};
+
+template <typename IN, typename IO>
 __global__ void __launch_bounds__(256)
-sdf_from_occupancy_kernel(const IO* __restrict__ im, int H, int W, int pad, double thresh, double res,
+sdf_from_occupancy_kernel(const IN* __restrict__ im, int H, int W, int pad, double thresh, double res,
                           IO* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
-  unsigned short* g0 = reinterpret_cast<unsigned short*>(smem_raw);   // distance in the column to the nearest OBSTACLE pixel
-  unsigned short* g1 = g0 + (size_t)Hp * Wp;                          // ... to the nearest FREE pixel
-  const IO* src = im + (size_t)blockIdx.x * H * W;
-  constexpr unsigned short INF = 65535;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad, NW = (Wp + 31) >> 5;
+  EdtSmem S;
+  S.m_obst = reinterpret_cast<unsigned*>(smem_raw);
+  S.m_free = S.m_obst + (size_t)Hp * NW;
+  S.g0 = reinterpret_cast<unsigned char*>(S.m_free + (size_t)Hp * NW);
+  S.g1 = S.g0 + (((size_t)Hp * Wp + 15) & ~(size_t)15);
+  const IN* src = im + (size_t)blockIdx.x * H * W;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // ---- A: row masks.  All pixels are fetched first (independent, coalesced loads; one DRAM latency for the image,
+  // not one per row) as one byte each into the area the envelope stacks use later, then one warp per row ballots them.
   int any_obst = 0, any_free = 0;
-  for (int x = threadIdx.x; x < Wp; x += blockDim.x) {
-    unsigned short d0 = INF, d1 = INF;
-    for (int y = 0; y < Hp; ++y) {                       // downward scan
-      const int yy = y - pad, xx = x - pad;
-      const bool inside = yy >= 0 && yy < H && xx >= 0 && xx < W;
-      const bool free_px = inside ? ((double)src[(size_t)yy * W + xx] > thresh) : true;   // padding is free space
-      d0 = free_px ? (d0 == INF ? INF : (unsigned short)(d0 + 1)) : 0;
-      d1 = free_px ? 0 : (d1 == INF ? INF : (unsigned short)(d1 + 1));
-      any_obst |= !free_px;
-      any_free |= free_px;
-      g0[(size_t)y * Wp + x] = d0;
-      g1[(size_t)y * Wp + x] = d1;
+  if constexpr (sizeof(IN) == sizeof(OccBits) && !std::is_arithmetic<IN>::value) {
+    // bit-packed input (pad == 0, checked by the host): the row masks ARE the input words
+    const unsigned* bits = reinterpret_cast<const unsigned*>(im) + (size_t)blockIdx.x * H * NW;
+    for (int i = threadIdx.x; i < Hp * NW; i += blockDim.x) {
+      const int c = i % NW;
+      const unsigned valid = (c == NW - 1 && (Wp & 31)) ? ((1u << (Wp & 31)) - 1u) : 0xffffffffu;
+      const unsigned bf = __ldg(bits + i) & valid, bo = ~bf & valid;
+      S.m_free[i] = bf; S.m_obst[i] = bo;
+      any_obst |= (bo != 0u);
+      any_free |= (bf != 0u);
     }
-    d0 = INF; d1 = INF;
-    for (int y = Hp - 1; y >= 0; --y) {                  // upward scan
-      const unsigned short a0 = g0[(size_t)y * Wp + x], a1 = g1[(size_t)y * Wp + x];
-      d0 = (a0 == 0) ? 0 : (d0 == INF ? INF : (unsigned short)(d0 + 1));
-      d1 = (a1 == 0) ? 0 : (d1 == INF ? INF : (unsigned short)(d1 + 1));
-      g0[(size_t)y * Wp + x] = min(a0, d0);
-      g1[(size_t)y * Wp + x] = min(a1, d1);
+  } else {
+    unsigned char* tmp = S.g1 + (((size_t)Hp * Wp + 15) & ~(size_t)15);
+#pragma unroll 8
+    for (int i = threadIdx.x; i < Hp * Wp; i += blockDim.x) {
+      const int y = i / Wp, x = i - y * Wp, yy = y - pad, xx = x - pad;
+      const bool inside = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      bool free_px = true;                                                                     // padding is free space
+      if constexpr (std::is_arithmetic<IN>::value) {
+        if (inside) free_px = (double)__ldg(src + (size_t)yy * W + xx) > thresh;
+      }
+      tmp[i] = free_px ? 1 : 0;
+    }
+    __syncthreads();
+    for (int y = warp; y < Hp; y += nwarps) {
+      for (int c = 0; c < NW; ++c) {
+        const int x = (c << 5) + lane;
+        const bool valid = x < Wp;
+        const bool free_px = valid && tmp[(size_t)y * Wp + (valid ? x : 0)] != 0;
+        const unsigned bf = __ballot_sync(0xffffffffu, free_px);
+        const unsigned bo = __ballot_sync(0xffffffffu, valid && !free_px);
+        if (lane == 0) { S.m_free[y * NW + c] = bf; S.m_obst[y * NW + c] = bo; }
+        any_obst |= (bo != 0u);
+        any_free |= (bf != 0u);
+      }
     }
   }
   const int has_obst = __syncthreads_or(any_obst);
   const int has_free = __syncthreads_or(any_free);
-  IO* dst = out + (size_t)blockIdx.x * Hp * Wp;
+  // ---- B: distance along the row, both polarities ----
   for (int i = threadIdx.x; i < Hp * Wp; i += blockDim.x) {
     const int y = i / Wp, x = i - y * Wp;
-    // A pixel is background of one of the two transforms (distance 0 there), so only ONE row scan is needed:
-    // free pixels look for the nearest obstacle (g0), obstacle pixels for the nearest free pixel (g1).
-    const bool is_free = g1[(size_t)y * Wp + x] == 0;
-    const unsigned short* r = (is_free ? g0 : g1) + (size_t)y * Wp;
-    // exact minimum over the row of dx^2 + g^2, scanned outwards from x: columns with dx^2 >= the best value so
-    // far cannot improve it.  32-bit integers suffice: Hp * Wp <= 58 112 by the shared-memory limit, so Hp^2 + Wp^2 < 2^32.
-    const unsigned a_c = r[x];
-    unsigned best = (a_c == INF) ? 0xffffffffu : a_c * a_c;
-    for (int k = 1; k < Wp; ++k) {
-      const unsigned k2 = (unsigned)k * (unsigned)k;
-      if (k2 >= best) break;
-      if (x - k >= 0) { const unsigned a = r[x - k]; if (a != INF) best = min(best, k2 + a * a); }
-      if (x + k < Wp) { const unsigned a = r[x + k]; if (a != INF) best = min(best, k2 + a * a); }
+    // a pixel is at distance 0 from its own polarity: one search per pixel, for the other polarity
+    const bool is_free = (S.m_free[y * NW + (x >> 5)] >> (x & 31)) & 1u;
+    const int d = edt_nearest_bit((is_free ? S.m_obst : S.m_free) + y * NW, NW, x);
+    S.g0[i] = (unsigned char)(is_free ? d : 0);
+    S.g1[i] = (unsigned char)(is_free ? 0 : d);
+  }
+  __syncthreads();
+  // ---- C: lower envelope per (column, polarity) ----
+  S.st_s = S.g1 + (((size_t)Hp * Wp + 15) & ~(size_t)15);
+  S.st_t = S.st_s + (size_t)Hp * blockDim.x;
+  IO* dst = out + (size_t)blockIdx.x * Hp * Wp;
+  const int NT = 2 * Wp;                                       // tasks: polarity * Wp + x
+  constexpr int BIG = 1 << 20;                                 // "no pixel of that polarity in this row": above every real value
+  for (int base = 0; base < NT; base += blockDim.x) {          // uniform trip count (one pass for Wp <= 128)
+    const int j = base + threadIdx.x;
+    const bool on = j < NT;
+    const int pol = on ? j / Wp : 0, x = on ? j - pol * Wp : 0;
+    const unsigned char* g = (pol == 0 ? S.g0 : S.g1) + x;     // column x of that polarity's row distances
+    unsigned char* ss = S.st_s + threadIdx.x;                  // (the stacks are reused by every batch of tasks)
+    unsigned char* tt = S.st_t + threadIdx.x;
+    const int SN = blockDim.x;
+    auto G = [&](int i) { const int a = g[(size_t)i * Wp]; return (a == 255) ? BIG : a * a; };
+    int q = 0, sq = 0, tq = 0, Gsq = 0;                        // top of the stack, cached in registers
+    if (on) {
+      Gsq = G(0);
+      ss[0] = 0; tt[0] = 0;
+      for (int u = 1; u < Hp; ++u) {
+        const int Gu = G(u);
+        // pop parabolas that the one at u beats at the start of their interval
+        while (q >= 0 && (tq - sq) * (tq - sq) + Gsq > (tq - u) * (tq - u) + Gu) {
+          --q;
+          if (q >= 0) { sq = ss[(size_t)q * SN]; tq = tt[(size_t)q * SN]; Gsq = G(sq); }
+        }
+        if (q < 0) {
+          q = 0; sq = u; tq = 0; Gsq = Gu;
+          ss[0] = (unsigned char)u; tt[0] = 0;
+        } else {
+          // Sep(sq, u) = floor((u^2 - sq^2 + Gu - Gsq) / (2 (u - sq))) >= tq >= 0: last row at which parabola sq is <= parabola u
+          const int num = u * u - sq * sq + Gu - Gsq, den = 2 * (u - sq);
+          int sep = (int)__fdividef((float)num, (float)den);
+          sep += ((sep + 1) * den <= num) ? 1 : 0;
+          sep -= (sep * den > num) ? 1 : 0;
+          const int w = 1 + sep;
+          if (w < Hp) {
+            ++q; sq = u; tq = w; Gsq = Gu;
+            ss[(size_t)q * SN] = (unsigned char)u; tt[(size_t)q * SN] = (unsigned char)w;
+          }
+        }
+      }
     }
-    // no background pixel at all: scipy (1.18) measures from a virtual pixel at row -1, column 0
-    const double quirk = sqrt((double)((long long)(y + 1) * (y + 1) + (long long)x * x));
-    const double d_scan = sqrt((double)best);
-    const double d_free = is_free ? (has_obst ? d_scan : quirk) : 0.0;     // EDT(im): free pixels -> nearest obstacle
-    const double d_obst = is_free ? 0.0 : (has_free ? d_scan : quirk);     // EDT(1 - im): obstacle pixels -> nearest free
-    dst[i] = (IO)((d_free - d_obst) * res);
+    // backward sweep, all tasks at the same row u: the lanes of a warp write consecutive pixels of that row
+    for (int u = Hp - 1; u >= 0; --u) {
+      if (on) {
+        const int d2 = (u - sq) * (u - sq) + Gsq;
+        const bool is_free = S.g1[(size_t)u * Wp + x] == 0;
+        if ((pol == 0) == is_free) {          // free pixels take the distance to the obstacles, obstacle pixels to free space
+          // EDT(im) for free pixels (-> nearest obstacle), EDT(1 - im) for obstacle pixels (-> nearest free pixel).  No
+          // background pixel at all (uniform): scipy (1.18) measures from a virtual pixel at row -1, column 0.
+          const bool have = is_free ? (has_obst != 0) : (has_free != 0);
+          const long long sq2 = have ? (long long)d2 : ((long long)(u + 1) * (u + 1) + (long long)x * x);
+          const double d = sqrt((double)sq2);
+          dst[(size_t)u * Wp + x] = (IO)((is_free ? d : (0.0 - d)) * res);
+        }
+        if (u == tq && q > 0) {
+          --q;
+          sq = ss[(size_t)q * SN]; tq = tt[(size_t)q * SN]; Gsq = G(sq);
+        }
+      }
+    }
   }
 }
 

@@ -1,7 +1,7 @@
 """Hinge-loss obstacle cost (API mirror of reference ``gpmp2/obstacle/obstacle_cost.py:7-38``).
 
-The SDF lookup runs in the CUDA library (dgpmp2_sdf_lookup_*); the hinge is two elementwise
-selects on its outputs.  Inside the GN step lookup + hinge + Jacobian are fused in one kernel.
+Lookup + hinge + gradient are ONE pass of the CUDA library (dgpmp2_hinge_batch_*: 8 bytes of position in, four
+SDF taps, 12 bytes out per point); inside the GN step the same arithmetic is fused into the assembly.
 """
 import torch
 
@@ -23,11 +23,19 @@ class HingeLossObstacleCost(object):
         x_lims, y_lims = self.env_params['x_lims'], self.env_params['y_lims']
         res = (x_lims[1] - x_lims[0]) / (sdfb.shape[-1])
         pts = to_cuda(sphere_centersb, dt).reshape(B, T * nl, 2)
-        dist, J = ops.sdf_lookup(to_cuda(sdfb, dt), pts, res, x_lims[0], y_lims[0])
-        eps_tot = (torch.as_tensor(epsb).to(dist.device, dt) + float(torch.as_tensor(r_vec).reshape(-1)[0])).reshape(-1, T * nl, 1)
-        active = dist <= eps_tot
-        cost = torch.where(active, eps_tot - dist, torch.zeros_like(dist))
-        H = torch.where(active, -1.0 * J, torch.zeros_like(J))
+        eps_t = torch.as_tensor(epsb)
+        r = float(torch.as_tensor(r_vec).reshape(-1)[0])
+        if eps_t.numel() == 1:
+            cost, H = ops.hinge_batch(to_cuda(sdfb, dt), pts, res, x_lims[0], y_lims[0], r, eps_const=float(eps_t))
+        else:
+            e = to_cuda(eps_t, dt)
+            if e.numel() == B * T * nl:
+                e = e.reshape(B, T * nl)
+            elif e.numel() == T * nl:
+                e = e.reshape(1, T * nl)
+            else:
+                e = torch.broadcast_to(e, (B, T, nl, 1)).reshape(B, T * nl)
+            cost, H = ops.hinge_batch(to_cuda(sdfb, dt), pts, res, x_lims[0], y_lims[0], r, eps=e)
         out_dt = sphere_centersb.dtype
         return (back(cost, sphere_centersb).to(out_dt).reshape(B, T, nl, 1),
                 back(H, sphere_centersb).to(out_dt).reshape(B, T, nl, 2))

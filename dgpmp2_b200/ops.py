@@ -265,11 +265,45 @@ def sdf_lookup(sdf, pts, res: float, x_lo: float, y_lo: float):
 
 
 @_on_tensor_device
+def hinge_batch(sdf, pts, res: float, x_lo: float, y_lo: float, r_sphere: float, eps=None, eps_const: float = 0.0):
+    """hinge_loss_signed_batch: sdf (B,H,W) / (B,1,H,W) / (1,H,W), pts (B,N,2), eps None (-> eps_const) or (B|1,N|1)
+    -> cost (B,N), He (B,N,2).  One fused pass: 36 algorithmic bytes per point (fp32)."""
+    _lib.require_cuda()
+    dt = pts.dtype
+    B, N, _ = pts.shape
+    pts = _prep(pts, dt, 'pts')
+    sdf3, sb = _sdf3(_prep(sdf, dt, 'sdf'), B)
+    esb = esn = 0
+    if eps is not None:
+        eps = _prep_w(eps, dt)
+        if eps.dim() != 2 or eps.shape[0] not in (1, B) or eps.shape[1] not in (1, N):
+            raise ValueError('eps must be (B|1, N|1), got %s' % (tuple(eps.shape),))
+        esb = 0 if eps.shape[0] == 1 else eps.stride(0)
+        esn = 0 if eps.shape[1] == 1 else eps.stride(1)
+    cost = torch.empty(B, N, dtype=dt, device=pts.device)
+    He = torch.empty(B, N, 2, dtype=dt, device=pts.device)
+    fn = getattr(load(), 'dgpmp2_hinge_batch_' + suffix(dt))
+    check(fn(ptr(sdf3), B, int(sdf3.shape[1]), int(sdf3.shape[2]), sb, ptr(pts), N, float(res), float(x_lo), float(y_lo),
+             ptr(eps), esb, esn, float(eps_const), float(r_sphere), ptr(cost), ptr(He), stream_ptr()))
+    return cost, He
+
+
+@_on_tensor_device
 def sdf_from_occupancy(im, padlen: int = 1, res: float = 1.0, thresh: float = 0.75):
-    """Batched signed distance field on the GPU: im (B,H,W) or (H,W) CUDA tensor -> (B,H+2p,W+2p), exact EDT."""
+    """Batched signed distance field on the GPU: im (B,H,W) or (H,W) CUDA tensor -> (B,H+2p,W+2p), exact EDT.
+    float32 / float64 images give an SDF of the same dtype; a uint8 image (free = im > thresh) gives float32."""
     _lib.require_cuda()
     if im.dim() == 2:
         im = im.unsqueeze(0)
+    if im.dtype == torch.uint8:
+        if not im.is_cuda:
+            raise _lib.Dgpmp2Error('im must be a CUDA tensor (no CPU path)')
+        im = im.contiguous()
+        B, H, W = im.shape
+        out = torch.empty(B, H + 2 * padlen, W + 2 * padlen, dtype=torch.float32, device=im.device)
+        check(load().dgpmp2_sdf_from_occupancy_u8_f32(ptr(im), B, H, W, int(padlen), float(thresh), float(res), ptr(out),
+                                                      stream_ptr()))
+        return out
     dt = im.dtype if im.dtype in (torch.float32, torch.float64) else torch.float32
     im = _prep(im, dt, 'im')
     B, H, W = im.shape
@@ -347,6 +381,63 @@ class HostStepper:
                      ptr(self.err), ptr(self.err_ext), ptr(self.status), ctypes.c_void_p(self.ws.data_ptr()), self.ws.numel(),
                      1 if sdf_resident else 0, stream_ptr()))
         self._sdf_staged = True
+        return self.dth, self.err, self.err_ext, self.status
+
+
+def pack_occupancy_bits(im, thresh: float = 0.75):
+    """(B,H,W) occupancy images (free = im > thresh; any dtype, host or device) -> (B,H,ceil(W/32)) int32 words, bit
+    (x & 31) of word x >> 5 set = FREE: the input layout of dgpmp2_sdf_from_occupancy_bits_f32 / HostOccStepper."""
+    free = (im > thresh)
+    B, H, W = free.shape
+    nw = (W + 31) // 32
+    if W != nw * 32:
+        free = torch.nn.functional.pad(free, (0, nw * 32 - W))
+    sh = (torch.ones(32, dtype=torch.int64, device=free.device) << torch.arange(32, dtype=torch.int64, device=free.device))
+    words = (free.reshape(B, H, nw, 32).to(torch.int64) * sh).sum(-1)
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)
+    return words.to(torch.int32).contiguous()
+
+
+@_on_tensor_device
+def sdf_from_occupancy_bits(bits, W: int, res: float = 1.0):
+    """Exact signed distance fields from bit-packed maps (pack_occupancy_bits): (B,H,ceil(W/32)) int32 -> (B,H,W) float32."""
+    _lib.require_cuda()
+    if not bits.is_cuda or bits.dtype != torch.int32:
+        raise _lib.Dgpmp2Error('bits must be a CUDA int32 tensor')
+    bits = bits.contiguous()
+    B, H, nw = bits.shape
+    if nw != (W + 31) // 32:
+        raise ValueError('bits has %d words per row, W = %d needs %d' % (nw, W, (W + 31) // 32))
+    out = torch.empty(B, H, W, dtype=torch.float32, device=bits.device)
+    check(load().dgpmp2_sdf_from_occupancy_bits_f32(ptr(bits), B, H, int(W), float(res), ptr(out), stream_ptr()))
+    return out
+
+
+class HostOccStepper(HostStepper):
+    """End-to-end GN step from HOST trajectories and HOST bit-packed occupancy maps (dgpmp2_gn_step_host_occ_f32): the maps
+    cross the bus as 1 bit per pixel and the signed distance fields are built on the device."""
+
+    def __init__(self, p: CParams, device=None):
+        super().__init__(p, torch.float32, device)
+        nbytes = ctypes.c_size_t(0)
+        check(load().dgpmp2_host_step_occ_workspace_bytes(ctypes.byref(p), ctypes.byref(nbytes)))
+        self.ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        self.occ_words = p.B * p.H * ((p.W + 31) // 32)
+        self.occ_bytes = 4 * self.occ_words
+
+    def step(self, th, start, goal, occ_bits):
+        p = self.p
+        B, T, d = p.B, p.T, 2 * p.dof
+        self._check_host(th, 'th', B * T * d)
+        self._check_host(start, 'start', B * d)
+        self._check_host(goal, 'goal', B * d)
+        if not isinstance(occ_bits, torch.Tensor) or occ_bits.is_cuda or occ_bits.dtype != torch.int32 or \
+                not occ_bits.is_contiguous() or occ_bits.numel() != self.occ_words:
+            raise ValueError('occ_bits must be a contiguous host int32 tensor of %d words (pack_occupancy_bits)' % self.occ_words)
+        with torch.cuda.device(self.device):
+            check(load().dgpmp2_gn_step_host_occ_f32(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(occ_bits), ptr(self.dth),
+                                                     ptr(self.err), ptr(self.err_ext), ptr(self.status),
+                                                     ctypes.c_void_p(self.ws.data_ptr()), self.ws.numel(), stream_ptr()))
         return self.dth, self.err, self.err_ext, self.status
 
 

@@ -70,6 +70,10 @@ def main(argv=None):
     ap.add_argument('--lr', type=float, default=0.02)
     ap.add_argument('--device', type=str, default='cuda', help="where the tensors live ('cpu': staged to the GPU per call)")
     ap.add_argument('--f64', action='store_true')
+    ap.add_argument('--ext-weight', type=float, default=1e-3,
+                    help='weight of the external loss gp + sg + lambda * obs of the final iterate (train_planner.py:327-346)')
+    ap.add_argument('--ext-obs-lambda', type=float, default=1.0)
+    ap.add_argument('--log', type=str, default=None, help='write per-step timings / checks as JSON (rank 0)')
     args = ap.parse_args(argv)
     rank, world, local_rank = parallel.init_distributed()
     dtype = torch.float64 if args.f64 else torch.float32
@@ -89,20 +93,67 @@ def main(argv=None):
     head = CovarianceHead(T, 4, 0.01, dtype).to(dev)
     planner.set_learn_module(head, 'diag_identity')
     opt = torch.optim.Adam(head.parameters(), lr=args.lr)
-    losses = []
+    losses, log = [], []
+    on_gpu = dev.type == 'cuda'
+    import torch.distributed as dist
+    n_allreduce = [0]
+    if dist.is_initialized():                                   # count the collectives issued per optimiser step
+        real_all_reduce = dist.all_reduce
+
+        def counting_all_reduce(*a, **k):
+            n_allreduce[0] += 1
+            return real_all_reduce(*a, **k)
+        dist.all_reduce = counting_all_reduce
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True) if on_gpu else None
+        if e is not None:
+            e.record()
+        return e
     for it in range(args.iters):
         opt.zero_grad()
         th = th0
+        t0 = ev()
         for _ in range(args.unroll):                       # truncated back-propagation through the planner
             dth = planner.step(th, start, goal, im, sdf)[0]
             th = th + dth
         loss = ((th - th_expert) ** 2).mean()
+        if args.ext_weight > 0.0:
+            # the reference's external loss on the final iterate: differentiable unweighted errors (train_planner.py:327-346)
+            e_sg, e_gp, e_obs = planner.unweighted_errors_batch(th, sdf)
+            loss = loss + args.ext_weight * (e_gp.mean() + e_sg.mean() + args.ext_obs_lambda * e_obs.mean())
+        t1 = ev()
         loss.backward()
+        t2 = ev()
+        n_allreduce[0] = 0
         n = parallel.allreduce_gradients(head.parameters())          # the only collective: one flat bucket
+        t3 = ev()
         opt.step()
         losses.append(float(loss.detach()))
+        rec = {'iter': it, 'loss': losses[-1], 'grad_elements': n, 'all_reduce_calls': n_allreduce[0]}
+        if on_gpu:
+            torch.cuda.synchronize()
+            rec.update(forward_ms=t0.elapsed_time(t1), backward_ms=t1.elapsed_time(t2), allreduce_ms=t2.elapsed_time(t3))
+        if world > 1:
+            assert n_allreduce[0] == 1, 'expected exactly one all-reduce per optimiser step, saw %d' % n_allreduce[0]
+            flat = torch.cat([p.detach().reshape(-1) for p in head.parameters()])
+            lo, hi = flat.clone(), flat.clone()
+            real_all_reduce(lo, op=dist.ReduceOp.MIN)
+            real_all_reduce(hi, op=dist.ReduceOp.MAX)
+            assert torch.equal(lo, hi), 'parameters differ between ranks after the optimiser step'
+            rec['params_identical_on_all_ranks'] = True
+        log.append(rec)
         if rank == 0:
-            print('iter %3d  imitation loss %.6f  (%d gradient elements all-reduced over %d rank(s))' % (it, losses[-1], n, world))
+            print('iter %3d  loss %.6f  (%d gradient elements all-reduced over %d rank(s)%s)' % (
+                it, losses[-1], n, world,
+                ', fwd %.2f ms bwd %.2f ms all-reduce %.3f ms' % (rec['forward_ms'], rec['backward_ms'], rec['allreduce_ms']) if on_gpu else ''))
+    if dist.is_initialized():
+        dist.all_reduce = real_all_reduce
+    if args.log and rank == 0:
+        import json
+        with open(args.log, 'w') as f:
+            json.dump({'world': world, 'batch_total': args.batch, 'batch_per_rank': int(th0.shape[0]), 'states': T, 'unroll': args.unroll,
+                       'backend': (dist.get_backend() if dist.is_initialized() else None), 'steps': log}, f, indent=1)
     return losses, head
 
 

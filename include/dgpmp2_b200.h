@@ -237,18 +237,43 @@ int dgpmp2_sdf_lookup_f64(const double* sdf, int32_t B, int32_t H, int32_t W, in
                           double* dist, double* J, void* stream);
 
 /*
+ * Hinge obstacle cost of a batch of sphere centres -- replaces HingeLossObstacleCost.hinge_loss_signed_batch
+ * (obstacle_cost.py:29-38) = bilinear_interpolate + the two torch.where selects, in one pass: per point 8 bytes of
+ * position in, four SDF taps, cost (4 bytes) and the 2-wide gradient H_e = -J (8 bytes) out (fp32 I/O).
+ *   pts (B,N,2) [2-element aligned], sdf (B,H,W) with problem stride sdf_stride_b (0 = shared)
+ *   eps: per-point margin with element strides (eps_stride_b, eps_stride_n), or NULL -> eps_const;
+ *   active when dist <= eps + r_sphere.   -> cost (B,N), He (B,N,2).
+ */
+int dgpmp2_hinge_batch_f32(const float* sdf, int32_t B, int32_t H, int32_t W, int64_t sdf_stride_b, const float* pts,
+                           int32_t N, double res, double x_lo, double y_lo, const float* eps, int64_t eps_stride_b,
+                           int64_t eps_stride_n, double eps_const, double r_sphere, float* cost, float* He, void* stream);
+int dgpmp2_hinge_batch_f64(const double* sdf, int32_t B, int32_t H, int32_t W, int64_t sdf_stride_b, const double* pts,
+                           int32_t N, double res, double x_lo, double y_lo, const double* eps, int64_t eps_stride_b,
+                           int64_t eps_stride_n, double eps_const, double r_sphere, double* cost, double* He, void* stream);
+
+/*
  * Signed distance field of a batch of occupancy images -- replaces sdf_2d (utils/sdf_utils.py:6-21,
  * datasets/utils.py:4-18: free = image > 0.75, optional padding with free cells, two
  * scipy.ndimage.distance_transform_edt calls, (edt(free) - edt(occupied)) * res).  Exact Euclidean
  * distance transform (integer squared distances, sqrt in double), including scipy's behaviour for
  * images without any background pixel.
  *   im (B,H,W) -> sdf_out (B, H+2*padlen, W+2*padlen); positive in free space.
- *   Limit: (H+2p)*(W+2p)*4 bytes of shared memory <= 227 KB (e.g. 238 x 238), else DGPMP2_ERR_UNSUPPORTED.
+ *   Limit: H+2p <= 254 and W+2p <= 254 (one-byte row distances), else DGPMP2_ERR_UNSUPPORTED.
  */
 int dgpmp2_sdf_from_occupancy_f32(const float* im, int32_t B, int32_t H, int32_t W, int32_t padlen, double thresh,
                                   double res, float* sdf_out, void* stream);
 int dgpmp2_sdf_from_occupancy_f64(const double* im, int32_t B, int32_t H, int32_t W, int32_t padlen, double thresh,
                                   double res, double* sdf_out, void* stream);
+/* Same with a uint8 occupancy image (free = im > thresh, e.g. 0 / 255 images with thresh 191.25 = 0.75 * 255): a quarter of
+ * the bytes of the float image when the maps come from the host. */
+int dgpmp2_sdf_from_occupancy_u8_f32(const uint8_t* im, int32_t B, int32_t H, int32_t W, int32_t padlen, double thresh,
+                                     double res, float* sdf_out, void* stream);
+
+/* Same from BIT-PACKED occupancy maps (padlen 0): row-major, every row padded to 32-bit words, bit (x & 31) of word
+ * x >> 5 set = pixel (y, x) is FREE.  1/32 of the bytes of the float SDF -- what makes shipping maps instead of SDFs
+ * across PCIe pay (dgpmp2_gn_step_host_occ_f32 below). */
+int dgpmp2_sdf_from_occupancy_bits_f32(const uint32_t* im_bits, int32_t B, int32_t H, int32_t W, double res, float* sdf_out,
+                                       void* stream);
 
 /*
  * The block-tridiagonal information system itself (what the reference holds as
@@ -277,6 +302,19 @@ int dgpmp2_gn_step_host_f32(const dgpmp2_params* p, const float* th, const float
 int dgpmp2_gn_step_host_f64(const dgpmp2_params* p, const double* th, const double* start, const double* goal,
                             const double* sdf, double* dth, double* err, double* err_ext, int32_t* status,
                             void* dev_ws, size_t dev_ws_bytes, int32_t sdf_resident, void* stream);
+
+/*
+ * End-to-end call from HOST trajectories and HOST bit-packed occupancy maps (layout as
+ * dgpmp2_sdf_from_occupancy_bits_f32; one H x W map per problem, p->sdf_stride_b == H*W): copies the inputs, builds the
+ * signed distance fields on the device (exact EDT, = sdf_2d(map, padlen=0, res=p->res), generate_2d_dataset.py:211),
+ * runs dgpmp2_gn_step_f32 and copies dth / err / err_ext / status back; synchronises the stream before returning.
+ * Replaces the host-side sdf_2d + the B*H*W*4-byte SDF transfer of the reference's data path by B*H*ceil(W/32)*4 bytes.
+ * `dev_ws`: at least dgpmp2_host_step_occ_workspace_bytes() bytes.
+ */
+int dgpmp2_host_step_occ_workspace_bytes(const dgpmp2_params* p, size_t* bytes);
+int dgpmp2_gn_step_host_occ_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal,
+                                const uint32_t* occ_bits, float* dth, float* err, float* err_ext, int32_t* status,
+                                void* dev_ws, size_t dev_ws_bytes, void* stream);
 
 /*
  * Launch-shape query for benchmarking / tests: problems per CTA, threads per CTA

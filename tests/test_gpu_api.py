@@ -214,6 +214,11 @@ def test_gpu_sdf_generation_bit_exact_vs_scipy_sdf_2d(H, W, pad):
         np.testing.assert_array_equal(got[k], ref)
     got32 = sdf_2d_gpu(torch.tensor(np.stack(ims), dtype=torch.float32), padlen=pad, res=res).cpu().numpy()
     np.testing.assert_allclose(got32, got, rtol=1e-6, atol=1e-6)
+    # uint8 occupancy images (a quarter of the bytes when the maps come from the host): same field in float32
+    from dgpmp2_b200 import ops
+    u8 = torch.tensor((np.stack(ims) > 0.75).astype(np.uint8) * 255).cuda()
+    got8 = ops.sdf_from_occupancy(u8, padlen=pad, res=res, thresh=0.75 * 255).cpu().numpy()
+    np.testing.assert_array_equal(got8, got32)
 
 
 def test_headless_batch_example_runs_end_to_end():

@@ -101,3 +101,31 @@ def test_host_step_validates_its_arguments():
     with pytest.raises(_lib.Dgpmp2Error):
         hs.step(th.cuda(), start, goal, sdf)
     hs.step(th, start, goal, sdf)
+
+
+def test_bit_packed_maps_give_the_same_field_and_the_same_step():
+    """dgpmp2_sdf_from_occupancy_bits_f32 == the float-image EDT (itself bit-identical to scipy's sdf_2d, test_gpu_api),
+    and dgpmp2_gn_step_host_occ_f32 (maps cross the bus as bits, SDF built on the device) == the host-SDF entry point."""
+    from dgpmp2_b200 import _lib, ops
+    from dgpmp2_b200.datasets.synthetic import make_problems
+    from tests.gpu_helpers import cparams
+    B, T = 37, 64
+    for size in (128, 100, 33):
+        pr = make_problems(B, T, im_size=size, seed=size, unique_envs=B)
+        im = pr['im'][:, 0].contiguous()
+        res = 10.0 / size
+        ref = ops.sdf_from_occupancy(im.cuda(), padlen=0, res=res)
+        bits = ops.pack_occupancy_bits(im)
+        got = ops.sdf_from_occupancy_bits(bits.cuda(), size, res=res)
+        assert torch.equal(got, ref)
+        cp = cparams(T, B=B, H=size, W=size)
+        _lib.set_sdf_shape(cp, size, size, size * size)
+        hs, ho = ops.HostStepper(cp, torch.float32), ops.HostOccStepper(cp)
+        th, start, goal = pr['th_init'].contiguous(), pr['start'].reshape(B, 4).contiguous(), pr['goal'].reshape(B, 4).contiguous()
+        a = [t.clone() for t in hs.step(th, start, goal, ref.cpu().contiguous())]
+        b = ho.step(th, start, goal, bits)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+        assert ho.occ_bytes == 4 * B * size * ((size + 31) // 32)
+    np_sdf = pr['sdf'][:, 0].numpy()
+    np.testing.assert_allclose(got.cpu().numpy(), np_sdf, rtol=1e-6, atol=1e-6)       # the dataset's scipy field
