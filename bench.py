@@ -232,15 +232,16 @@ def live_anchor():
         return {'value': None, 'note': 'reference tree not on this box (pure-Python reference, not installable; measured in the '
                                        'build container: profiles/r02_live_reference_anchor.json)'}
     out = []
-    for sample_B, threads in ((1, 1), (2, 1), (4, 1)):
-        r, why = run_child('live-worker', 3, 1, sample_B, 150, ['--live-threads', str(threads)])
+    for sample_B, threads, limit in ((1, 1, 120), (4, 1, 120), (16, 1, 150), (32, 1, 150), (8, host_threads(), 60)):
+        r, why = run_child('live-worker', 3, 1, sample_B, limit, ['--live-threads', str(threads)])
         if r is None or 'unavailable' in (r or {}):
             out.append({'sample_B': sample_B, 'threads': threads, 'value': 'timeout' if r is None else None, 'why': why or r.get('unavailable')})
         else:
             out.append({'sample_B': sample_B, 'threads': r['threads'], 'value': r['value'], 'sec_per_step': r['sec_per_step']})
     best = max((o['value'] for o in out if isinstance(o['value'], float)), default=None)
     return {'value': best, 'unit': UNIT, 'runs': out,
-            'what': 'LIVE reference DiffGPMP2Planner.step (diff_gpmp2_planner.py:176-211), fp64, same synthetic workload'}
+            'what': 'LIVE reference DiffGPMP2Planner.step (diff_gpmp2_planner.py:176-211), fp64, same synthetic workload; '
+                    'single-threaded chunks run, multi-threaded ones hang in MKL batched getrf/getri (torch.inverse) on these hosts'}
 
 
 def cpu_baseline_obj(r):

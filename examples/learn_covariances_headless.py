@@ -58,7 +58,10 @@ class CovarianceHead(nn.Module):
         self.register_buffer('base', base)
 
     def forward(self, th, im, sdf):
-        return (self.base * torch.exp(self.lin(th.reshape(th.shape[0], -1)))).unsqueeze(1)
+        # bounded relative steps: every raw output stays within exp(+-1) of the planner's constant, whatever the optimiser
+        # does (an unbounded exp() of T*d inputs overflows the obstacle weight after one Adam step at T = 64)
+        x = th.reshape(th.shape[0], -1) / float(th.shape[1] * th.shape[2])
+        return (self.base * torch.exp(torch.tanh(self.lin(x)))).unsqueeze(1)
 
 
 def main(argv=None):
@@ -73,7 +76,7 @@ def main(argv=None):
     ap.add_argument('--ext-weight', type=float, default=1e-3,
                     help='weight of the external loss gp + sg + lambda * obs of the final iterate (train_planner.py:327-346)')
     ap.add_argument('--ext-obs-lambda', type=float, default=1.0)
-    ap.add_argument('--log', type=str, default=None, help='write per-step timings / checks as JSON (rank 0)')
+    ap.add_argument('--json-out', dest='log', type=str, default=None, help='write per-step timings / checks as JSON (rank 0)')
     args = ap.parse_args(argv)
     rank, world, local_rank = parallel.init_distributed()
     dtype = torch.float64 if args.f64 else torch.float32

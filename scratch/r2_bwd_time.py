@@ -17,16 +17,18 @@ dth = ops.gn_step(cp, th, start, goal, sdf)[0]
 g = torch.randn_like(dth)
 
 
-def timed(fn, n=30):
+def timed(fn, n=20):
     for _ in range(3): fn()
     torch.cuda.synchronize()
+    g_ = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_):
+        for _ in range(n): fn()
+    g_.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n): fn()
-    e1.record(); torch.cuda.synchronize()
+    e0.record(); g_.replay(); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
 
-out = {'forward static (us, eager incl. allocation)': timed(lambda: ops.gn_step(cp, th, start, goal, sdf)),
+out = {'forward static (us)': timed(lambda: ops.gn_step(cp, th, start, goal, sdf)),
        'forward learned weights (us)': timed(lambda: ops.gn_step(cp, th, start, goal, sdf, qc_inv=qc, w_obs=w, eps=eps)),
        'backward g_th only (us)': timed(lambda: ops.gn_step_backward(cp, th, start, goal, sdf, dth, g, None, need_th=True)),
        'backward all seven gradients (us)': timed(lambda: ops.gn_step_backward(
