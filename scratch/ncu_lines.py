@@ -25,7 +25,7 @@ for r in rows[2:]:
     op = txt.split()[1] if txt.startswith('@') else txt.split()[0]
     ops[op.split('.')[0]] += n
 src = {}
-for f in ('bcr.cuh', 'kernels.cuh', 'factors.cuh', 'bcr_plan.cuh'):
+for f in ('bcr.cuh', 'kernels.cuh', 'factors.cuh', 'bcr_plan.cuh', 'hd.cuh', 'mp.cuh'):
     src[f] = open('/root/repo/dgpmp2_b200/csrc/' + f).read().split('\n')
 print('total warp instructions', tot)
 print('opcode mix:', ', '.join('%s %.1f%%' % (k, 100 * v / tot) for k, v in ops.most_common(22)))
