@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libdgpmp2_b200.so')
 SOURCES = ['c_abi.cu']
-DEPS = ['c_abi.cu', 'kernels.cuh', 'bcr.cuh', 'bcr_plan.cuh', 'factors.cuh', os.path.join('..', '..', 'include', 'dgpmp2_b200.h')]
+DEPS = ['c_abi.cu', 'kernels.cuh', 'bcr.cuh', 'bcr_plan.cuh', 'factors.cuh', 'mp.cuh', 'hd.cuh', os.path.join('..', '..', 'include', 'dgpmp2_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared', '--cudart', 'static']
 

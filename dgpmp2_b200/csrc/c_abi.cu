@@ -475,6 +475,28 @@ HostWs host_ws_layout(const dgpmp2_params* p, size_t es) {
   return w;
 }
 
+// Two helper streams per device for the chunked host step (created once, kept for the life of the process).
+struct HostPipe { cudaStream_t s[2]; cudaEvent_t ready, done[2]; bool ok; std::mutex busy; };
+
+HostPipe* host_pipe() {
+  static std::mutex mu;
+  static HostPipe pipes[64];
+  static bool made[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!made[dev]) {
+    HostPipe& h = pipes[dev];
+    h.ok = cudaStreamCreateWithFlags(&h.s[0], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&h.s[1], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h.ready, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h.done[0], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&h.done[1], cudaEventDisableTiming) == cudaSuccess;
+    made[dev] = true;
+  }
+  return pipes[dev].ok ? &pipes[dev] : nullptr;
+}
+
 template <typename IO>
 int gn_step_host_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO* goal, const IO* sdf, IO* dth,
                       IO* err, IO* err_ext, int32_t* status, void* dev_ws, size_t dev_ws_bytes, int32_t sdf_resident,
@@ -490,6 +512,52 @@ int gn_step_host_impl(const dgpmp2_params* p, const IO* th, const IO* start, con
   unsigned char* ws = static_cast<unsigned char*>(dev_ws);
   const size_t B = p->B, T = p->T, d = 2 * p->dof;
   const size_t sdf_elems = (p->sdf_stride_b == 0) ? (size_t)p->H * p->W : (size_t)p->sdf_stride_b * B;
+  // Chunked pipeline (per-problem SDFs copied every step, enough problems): the batch is cut into chunks that alternate
+  // between two helper streams, so chunk c's kernel and device-to-host copies overlap chunk c+1's host-to-device copy
+  // (the two directions use different copy engines).  A problem's result does not depend on the batch it is launched
+  // in, so the output is bit-identical to the one-launch path.  Opt-in (DGPMP2_HOST_CHUNKS=n > 1): measured on B200 it
+  // does not pay -- the 64 MiB SDF copy alone saturates PCIe (1024 problems: 763 k problem-iters/s in one piece, 741 k
+  // in 4 chunks, 683 k in 8; profiles/r02_host_chunks_ab.txt), the kernel and the 1 MB of results are < 3 % of the step.
+  const int want_chunks = env_int("DGPMP2_HOST_CHUNKS", 1);
+  HostPipe* hp = (want_chunks > 1 && !sdf_resident && p->sdf_stride_b > 0 && B >= 256) ? host_pipe() : nullptr;
+  if (hp != nullptr) {
+    std::lock_guard<std::mutex> in_use(hp->busy);      // the helper streams / events serve one (synchronous) call at a time
+    const size_t nch = (size_t)want_chunks;
+    CUDA_TRY(cudaEventRecord(hp->ready, st));
+    for (int k = 0; k < 2; ++k) CUDA_TRY(cudaStreamWaitEvent(hp->s[k], hp->ready, 0));
+    for (size_t c = 0; c < nch; ++c) {
+      const size_t lo = B * c / nch, hi = B * (c + 1) / nch, nb = hi - lo;
+      if (nb == 0) continue;
+      cudaStream_t cs = hp->s[c & 1];
+      IO* d_th = reinterpret_cast<IO*>(ws + L.th) + lo * T * d;
+      IO* d_start = reinterpret_cast<IO*>(ws + L.start) + lo * d;
+      IO* d_goal = reinterpret_cast<IO*>(ws + L.goal) + lo * d;
+      IO* d_sdf = reinterpret_cast<IO*>(ws + L.sdf) + lo * (size_t)p->sdf_stride_b;
+      IO* d_dth = reinterpret_cast<IO*>(ws + L.dth) + lo * T * d;
+      IO* d_err = reinterpret_cast<IO*>(ws + L.err) + lo;
+      IO* d_ee = reinterpret_cast<IO*>(ws + L.err_ext) + lo;
+      int32_t* d_st = reinterpret_cast<int32_t*>(ws + L.status) + lo;
+      CUDA_TRY(cudaMemcpyAsync(d_th, th + lo * T * d, nb * T * d * sizeof(IO), cudaMemcpyHostToDevice, cs));
+      CUDA_TRY(cudaMemcpyAsync(d_start, start + lo * d, nb * d * sizeof(IO), cudaMemcpyHostToDevice, cs));
+      CUDA_TRY(cudaMemcpyAsync(d_goal, goal + lo * d, nb * d * sizeof(IO), cudaMemcpyHostToDevice, cs));
+      CUDA_TRY(cudaMemcpyAsync(d_sdf, sdf + lo * (size_t)p->sdf_stride_b, nb * (size_t)p->sdf_stride_b * sizeof(IO),
+                               cudaMemcpyHostToDevice, cs));
+      dgpmp2_params q = *p;
+      q.B = (int32_t)nb;
+      rc = gn_step_impl<IO>(&q, d_th, d_start, d_goal, d_sdf, nullptr, d_dth, d_err, d_ee, d_st, cs);
+      if (rc != DGPMP2_OK) return rc;
+      CUDA_TRY(cudaMemcpyAsync(dth + lo * T * d, d_dth, nb * T * d * sizeof(IO), cudaMemcpyDeviceToHost, cs));
+      CUDA_TRY(cudaMemcpyAsync(err + lo, d_err, nb * sizeof(IO), cudaMemcpyDeviceToHost, cs));
+      CUDA_TRY(cudaMemcpyAsync(err_ext + lo, d_ee, nb * sizeof(IO), cudaMemcpyDeviceToHost, cs));
+      if (status) CUDA_TRY(cudaMemcpyAsync(status + lo, d_st, nb * 4, cudaMemcpyDeviceToHost, cs));
+    }
+    for (int k = 0; k < 2; ++k) {
+      CUDA_TRY(cudaEventRecord(hp->done[k], hp->s[k]));
+      CUDA_TRY(cudaStreamWaitEvent(st, hp->done[k], 0));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return DGPMP2_OK;
+  }
   CUDA_TRY(cudaMemcpyAsync(ws + L.th, th, B * T * d * sizeof(IO), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(ws + L.start, start, B * d * sizeof(IO), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(ws + L.goal, goal, B * d * sizeof(IO), cudaMemcpyHostToDevice, st));
@@ -506,7 +574,6 @@ int gn_step_host_impl(const dgpmp2_params* p, const IO* th, const IO* start, con
   CUDA_TRY(cudaStreamSynchronize(st));
   return DGPMP2_OK;
 }
-
 
 // End to end from bit-packed occupancy maps: H2D of the trajectories and of B*H*ceil(W/32) words of map bits (1/32 of
 // the float SDF), exact EDT on the device into the workspace's SDF region, GN step, D2H of the results.

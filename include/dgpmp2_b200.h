@@ -294,6 +294,11 @@ int dgpmp2_band_f64(const dgpmp2_params* p, const double* th, const double* star
  * at least dgpmp2_host_step_workspace_bytes() bytes.  Weights must be static
  * (w == NULL).  If `sdf_resident` is non-zero the SDF copy is skipped and the SDF
  * already in the workspace (from a previous call with the same shape) is reused.
+ * Opt-in (environment DGPMP2_HOST_CHUNKS=n > 1, per-problem SDFs, B >= 256): the batch is processed in n chunks that
+ * alternate between two library-owned helper streams (created once per device, the only process-wide state of the
+ * library; calls are serialised on them), so that one chunk's kernel and device-to-host copies overlap the next
+ * chunk's host-to-device copy; the helper streams are ordered after `stream` on entry and `stream` after them on
+ * exit.  Results are bit-identical to the one-launch path.  Off by default: the SDF copy saturates PCIe either way.
  */
 int dgpmp2_host_step_workspace_bytes(const dgpmp2_params* p, int32_t elem_size, size_t* bytes);
 int dgpmp2_gn_step_host_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal,

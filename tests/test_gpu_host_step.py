@@ -129,3 +129,35 @@ def test_bit_packed_maps_give_the_same_field_and_the_same_step():
         assert ho.occ_bytes == 4 * B * size * ((size + 31) // 32)
     np_sdf = pr['sdf'][:, 0].numpy()
     np.testing.assert_allclose(got.cpu().numpy(), np_sdf, rtol=1e-6, atol=1e-6)       # the dataset's scipy field
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+def test_chunked_host_step_is_bit_identical(dtype):
+    """B >= 256 with per-problem SDFs: the host entry point pipelines 4 chunks over two helper streams; same bits as the
+    single-launch path (DGPMP2_HOST_CHUNKS=1) and as the device-resident entry point, pinned or pageable buffers."""
+    import os
+    from dgpmp2_b200 import _lib, ops
+    from dgpmp2_b200.datasets.synthetic import make_problems
+    from tests.gpu_helpers import cparams
+    B, T = 301, 64
+    pr = make_problems(B, T, im_size=64, seed=9, unique_envs=16, dtype=dtype)
+    cp = cparams(T, B=B, H=64, W=64)
+    _lib.set_sdf_shape(cp, 64, 64, 64 * 64)
+    hs = ops.HostStepper(cp, dtype)
+    th, start, goal, sdf = pr['th_init'].contiguous(), pr['start'].reshape(B, 4).contiguous(), pr['goal'].reshape(B, 4).contiguous(), pr['sdf'][:, 0].contiguous()
+    ref = [t.cpu() for t in ops.gn_step(cparams(T), th.cuda(), start.cuda(), goal.cuda(), sdf.cuda())]
+    saved = os.environ.pop('DGPMP2_HOST_CHUNKS', None)
+    try:
+        for pinned in (False, True):
+            args = [t.pin_memory() if pinned else t for t in (th, start, goal, sdf)]
+            for chunks in (None, '1', '7'):
+                os.environ.pop('DGPMP2_HOST_CHUNKS', None)
+                if chunks:
+                    os.environ['DGPMP2_HOST_CHUNKS'] = chunks
+                out = hs.step(*args)
+                for a, b in zip(out, ref):
+                    assert torch.equal(a, b), (pinned, chunks)
+    finally:
+        os.environ.pop('DGPMP2_HOST_CHUNKS', None)
+        if saved is not None:
+            os.environ['DGPMP2_HOST_CHUNKS'] = saved
