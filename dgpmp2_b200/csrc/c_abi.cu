@@ -46,7 +46,7 @@ int check_params(const dgpmp2_params* p, const dgpmp2_weights* w) {
   return DGPMP2_OK;
 }
 
-struct LaunchShape { int np, tpp, threads, smem, grid; };
+struct LaunchShape { int np, tpp, threads, smem, grid, n_big; };   // CTAs [0, n_big) take np problems, the others np - 1
 
 int sm_count() {
   static int cached[64] = {0};
@@ -65,15 +65,27 @@ int sm_count() {
 // of all of them are packed onto consecutive lanes, so the sparse deep levels of several problems
 // share warps, and one CTA per SM launches without a ramp.  Threads = kLPN lanes per level-1 item
 // when that fits the CTA, else one thread per node record.
+//
+// balanced (gn_step_kernel): when an SM's share q = ceil(B / #SMs) does not fit one CTA, it is cut into
+// w = ceil(q / np_max) CTAs of as equal a size as possible -- np = ceil(q / w) problems in the first CTA(s) an SM
+// receives, np - 1 in the later ones (the hardware hands out CTAs in index order) -- instead of w CTAs of np_max with
+// a ragged last wave: T = 128, B = 1024 runs 148 x 4 + 144 x 3 problems instead of 256 x 4 in waves of 148 + 108.
 template <int D, typename IO>
-int choose_shape(int B, int T, int mode, LaunchShape& s) {
+int choose_shape(int B, int T, int mode, LaunchShape& s, bool balanced = false) {
   const int max_threads = (D == 4) ? 512 : 256;
   const int items = (T + 1) / 2;                 // level-1 work items (and assembly needs T threads ~ 2 * items)
-  int np = (B + sm_count() - 1) / sm_count();
-  np = env_int("DGPMP2_NP", np);
+  const int q = (B + sm_count() - 1) / sm_count();
+  int np = env_int("DGPMP2_NP", q);
   if (np > B) np = B;
   if (np < 1) np = 1;
   while (np > 1 && StepSmem<D, IO>::bytes(np, T, mode) > (size_t)kSmemLimit) --np;
+  int big_waves = -1;                            // -1: every CTA takes np problems
+  if (balanced && np < q && env_int("DGPMP2_BALANCED", 1) == 1 && getenv("DGPMP2_NP") == nullptr) {
+    const int w = (q + np - 1) / np;
+    np = (q + w - 1) / w;                        // <= the shared-memory bound found above
+    big_waves = q - w * (np - 1);                // q = big_waves * np + (w - big_waves) * (np - 1)
+    if (np == 1 || big_waves >= w) big_waves = -1;
+  }
   const size_t bytes = StepSmem<D, IO>::bytes(np, T, mode);
   if (bytes > (size_t)kSmemLimit) return DGPMP2_ERR_UNSUPPORTED;
   int threads = kLPN * items * np;
@@ -91,6 +103,14 @@ int choose_shape(int B, int T, int mode, LaunchShape& s) {
   s.threads = threads;
   s.smem = (int)bytes;
   s.grid = (B + np - 1) / np;
+  s.n_big = s.grid;
+  if (big_waves >= 0) {
+    const long long cap_big = (long long)sm_count() * big_waves * np;
+    if (cap_big < B) {
+      s.n_big = sm_count() * big_waves;
+      s.grid = s.n_big + (int)((B - cap_big + np - 2) / (np - 1));
+    }
+  }
   return DGPMP2_OK;
 }
 
@@ -118,7 +138,7 @@ template <int DOF, typename IO>
 int launch_step(const KParams& k, const KWeights<IO>& kw, const IO* th, const IO* start, const IO* goal, const IO* sdf,
                 IO* dth, IO* err, IO* err_ext, int32_t* status, cudaStream_t st) {
   LaunchShape s;
-  int rc = choose_shape<2 * DOF, IO>(k.B, k.T, 0, s);
+  int rc = choose_shape<2 * DOF, IO>(k.B, k.T, 0, s, true);
   if (rc != DGPMP2_OK) return rc;
   auto kern = gn_step_kernel<DOF, IO>;
   rc = allow_smem(kern, s.smem);
@@ -136,10 +156,10 @@ int launch_step(const KParams& k, const KWeights<IO>& kw, const IO* th, const IO
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, k, kw, th, start, goal, sdf, dth, err, err_ext, status, s.np));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, k, kw, th, start, goal, sdf, dth, err, err_ext, status, s.np, s.n_big));
     return DGPMP2_OK;
   }
-  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, s.np);
+  kern<<<s.grid, s.threads, s.smem, st>>>(k, kw, th, start, goal, sdf, dth, err, err_ext, status, s.np, s.n_big);
   CUDA_TRY(cudaGetLastError());
   return DGPMP2_OK;
 }
@@ -825,8 +845,8 @@ int dgpmp2_gn_step_launch_shape(const dgpmp2_params* p, int32_t elem_size, int32
       return DGPMP2_OK;
     }
   }
-  if (p->dof == 2) rc = (elem_size == 4) ? choose_shape<4, float>(B, p->T, 0, s) : choose_shape<4, double>(B, p->T, 0, s);
-  else rc = (elem_size == 4) ? choose_shape<6, float>(B, p->T, 0, s) : choose_shape<6, double>(B, p->T, 0, s);
+  if (p->dof == 2) rc = (elem_size == 4) ? choose_shape<4, float>(B, p->T, 0, s, true) : choose_shape<4, double>(B, p->T, 0, s, true);
+  else rc = (elem_size == 4) ? choose_shape<6, float>(B, p->T, 0, s, true) : choose_shape<6, double>(B, p->T, 0, s, true);
   if (rc != DGPMP2_OK) return rc;
   if (problems_per_cta) *problems_per_cta = s.np;
   if (threads) *threads = s.threads;

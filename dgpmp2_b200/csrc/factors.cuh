@@ -30,7 +30,7 @@ struct KParams {
   // Host-precomputed GP blocks for the static case (no per-(b,t) Qc^-1, not Q_FULL): row-major d x d.
   int static_gp;        // 1: use Qs / PQs / PQPs below instead of building them per state
   int ext_same;         // 1: err_ext == err (static weights equal to the constructor-time ones)
-  int prefetch;         // 1: L2 prefetch of the SDF rows ahead of the assembly arithmetic (kernels.cuh: assemble_cta)
+  int prefetch;         // L2 prefetch of the SDF rows: bit 0 ahead of the assembly arithmetic (kernels.cuh: assemble_cta), bit 1 at the top of gn_step_kernel instead
   int fuse1;            // 1: gn_step_kernel eliminates the level-1 nodes inside the assembly (kernels.cuh: assemble_cta)
   double Qs[36];        // Q^-1 from qc_const
   double PQs[36];       // Phi^T Q^-1

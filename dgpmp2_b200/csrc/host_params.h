@@ -65,7 +65,11 @@ inline KParams make_kparams(const dgpmp2_params* p) {
     }
   k.static_gp = 0;   // set by the caller once the weights are known
   k.ext_same = 0;
-  k.prefetch = (env_int("DGPMP2_PREFETCH", 1) == 1) ? 1 : 0;      // DGPMP2_PREFETCH=2 disables the SDF prefetch (A/B)
+  {  // SDF L2 prefetch (bit 0: inside the assembly, bit 1: gn_step_kernel issues it at its top instead).  DGPMP2_PREFETCH:
+     // 1 / unset = default (early in the step kernel, in the assembly elsewhere), 2 = off, 3 = in the assembly everywhere (A/B)
+    const int pf = env_int("DGPMP2_PREFETCH", 1);
+    k.prefetch = (pf == 1) ? 3 : (pf == 3) ? 1 : 0;
+  }
   k.mp_accept = ldexpf(1.0f, -env_int("DGPMP2_MP_ACCEPT_LOG2", 17));
   bcr_make_plan(p->T, env_int("DGPMP2_TAIL", kTailMaxDefault), env_int("DGPMP2_WIDE", kWideMinDefault), k.plan);
   return k;

@@ -65,11 +65,12 @@ template <int DOF, typename IO>
 __device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO>& Wt, const StepSmem<2 * DOF, IO>& S,
                                              int b0, int np,
                                              const IO* __restrict__ start, const IO* __restrict__ goal,
-                                             const IO* __restrict__ sdf, bool fuse1 = false) {
+                                             const IO* __restrict__ sdf, bool fuse1 = false, bool prefetch = true) {
   constexpr int D = 2 * DOF;
   using N = Node<D>;
   const int T = P.T;
   const float inv_T = P.plan.inv_T;
+  prefetch = prefetch && (P.prefetch & 1);
   for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
     const int p = fast_div(m, inv_T), slot = m - p * T;
     const int t = bcr_state_of_slot(T, slot);
@@ -82,7 +83,7 @@ __device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO
       thp[a] = (t > 0) ? (double)tp[a - D] : 0.0;
       thn[a] = (t < T - 1) ? (double)tp[a + D] : 0.0;
     }
-    if (P.prefetch) {
+    if (prefetch) {
       // L2 prefetch of the two SDF rows this state's obstacle factor gathers from, issued before the prior / GP arithmetic
       // so that the DRAM latency of the (DRAM-cold) gather hides behind it.  A hint only: the pixel is located in float
       // arithmetic (the exact, branch-deciding location is computed in double inside assemble_node); no register is
@@ -247,15 +248,18 @@ template <int DOF, typename IO>
 __global__ void __launch_bounds__(DOF == 2 ? 512 : 256)
 gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th, const IO* __restrict__ start,
                const IO* __restrict__ goal, const IO* __restrict__ sdf, IO* __restrict__ dth,
-               IO* __restrict__ err, IO* __restrict__ err_ext, int* __restrict__ status, const int NP) {
+               IO* __restrict__ err, IO* __restrict__ err_ext, int* __restrict__ status, const int NP,
+               const int n_big) {
   constexpr int D = 2 * DOF;
   using N = Node<D>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StepSmem<D, IO> S;
   const int T = P.T;
   S.carve(smem_raw, NP, T, 0);
-  const int b0 = blockIdx.x * NP;
-  const int np = min(NP, P.B - b0);
+  // CTAs [0, n_big) take NP problems each, the later ones NP - 1 (c_abi.cu: choose_shape, balanced waves)
+  const int small = max((int)blockIdx.x - n_big, 0);
+  const int b0 = blockIdx.x * NP - small;
+  const int np = min(NP - ((int)blockIdx.x >= n_big ? 1 : 0), P.B - b0);
   // Programmatic dependent launch (c_abi.cu: launch_step): let the next launch of the stream be scheduled onto the
   // SMs as soon as this grid's CTAs leave them, and wait here -- before the first global access -- until the
   // previous grid of the stream has completed and its writes are visible.  Both are no-ops for a plain launch.
@@ -263,12 +267,29 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
   asm volatile("griddepcontrol.wait;" ::: "memory");
   DGPMP2_STAMP(0);
 
+  const bool early = (P.prefetch & 2) != 0;
+  if (early) {
+    // Early SDF prefetch (measured DRAM-cold, B=1024: 19.16 -> 18.21 us at T=64, 38.0 -> 36.4 us at T=128): every thread reads the position of one state straight from
+    // global memory (natural order, coalesced; the staging loads below then hit L1 / L2) and requests the two SDF rows of
+    // its obstacle factor before the trajectory is staged, so the DRAM-cold gather starts one barrier earlier.
+    const IO* src = th + (size_t)b0 * T * D;
+    const float inv_T = P.plan.inv_T;
+    for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
+      const int p = fast_div(m, inv_T);
+      const float fx = (float)P.orig_x + (float)__ldg(src + (size_t)m * D) * (float)P.inv_res;
+      const float fy = (float)P.orig_y - (float)__ldg(src + (size_t)m * D + 1) * (float)P.inv_res;
+      const int ix = min(max(__float2int_rd(fx), 0), P.W - 1), iy = min(max(__float2int_rd(fy), 0), P.H - 1);
+      const IO* q = sdf + (size_t)(b0 + p) * P.sdf_sb + (size_t)iy * P.W + ix;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(q + ((iy + 1 < P.H) ? P.W : 0)));
+    }
+  }
   cta_prologue<D, IO>(P, S, T, NP, np, th + (size_t)b0 * T * D, false);
   __syncthreads();
   DGPMP2_STAMP(1);
 
   const bool fuse1 = P.fuse1 != 0;      // uniform (host: static GP blocks and at least one elimination level)
-  assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf, fuse1);
+  assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf, fuse1, !early);
   __syncthreads();
   DGPMP2_STAMP(2);
 

@@ -324,6 +324,8 @@ int dgpmp2_gn_step_host_occ_f32(const dgpmp2_params* p, const float* th, const f
 /*
  * Launch-shape query for benchmarking / tests: problems per CTA, threads per CTA
  * and dynamic shared-memory bytes the GN-step kernel will use for these params.
+ * When an SM's share of the batch does not fit one CTA the grid holds CTAs of two sizes
+ * (`problems_per_cta` in the first ones, one fewer in the later ones: balanced waves).
  */
 int dgpmp2_gn_step_launch_shape(const dgpmp2_params* p, int32_t elem_size,
                                 int32_t* problems_per_cta, int32_t* threads, int32_t* smem_bytes, int32_t* grid);

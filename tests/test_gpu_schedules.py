@@ -96,3 +96,32 @@ def test_level1_elimination_fused_into_the_assembly_is_bit_identical(dtype):
         os.environ.pop('DGPMP2_FUSE1', None)
         if saved is not None:
             os.environ['DGPMP2_FUSE1'] = saved
+
+
+@pytest.mark.parametrize('dof,T,B', [(2, 128, 1000), (2, 128, 593), (3, 96, 300), (2, 64, 1333)])
+def test_balanced_waves_give_the_same_bits_and_cover_every_problem(dof, T, B):
+    """When an SM's share of the batch does not fit one CTA, gn_step_kernel runs CTAs of np and np - 1 problems
+    (c_abi.cu: choose_shape, balanced).  A problem's result does not depend on the CTA it lands in: identical bits to
+    the uniform grid (DGPMP2_BALANCED=2), every problem written exactly once (NaN-filled outputs, ragged last CTA)."""
+    from dgpmp2_b200 import ops
+    from dgpmp2_b200.datasets.synthetic import make_problems
+    from tests.gpu_helpers import cparams
+    base = XYH if dof == 3 else YAML
+    pr = make_problems(B, T, dof=dof, unique_envs=5, seed=B + T, im_size=48)
+    th, start, goal, sdf = (pr[k].cuda().float() for k in ('th_init', 'start', 'goal', 'sdf'))
+    cp = cparams(T, base=base, dof=dof, non_holonomic=(dof == 3))
+    saved = os.environ.pop('DGPMP2_BALANCED', None)
+    try:
+        shape_bal = ops.launch_shape(cparams(T, B=B, base=base, dof=dof, non_holonomic=(dof == 3)))
+        got = ops.gn_step(cp, th, start, goal, sdf)
+        os.environ['DGPMP2_BALANCED'] = '2'
+        shape_uni = ops.launch_shape(cparams(T, B=B, base=base, dof=dof, non_holonomic=(dof == 3)))
+        ref = ops.gn_step(cp, th, start, goal, sdf)
+    finally:
+        os.environ.pop('DGPMP2_BALANCED', None)
+        if saved is not None:
+            os.environ['DGPMP2_BALANCED'] = saved
+    assert int(ref[3].abs().max()) == 0 and bool(torch.isfinite(ref[0]).all())
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    print(shape_bal, shape_uni)
