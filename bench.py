@@ -14,8 +14,9 @@ value = N * B * K / max-over-ranks(time).
 
 Printed JSON (one line, rank 0):
   value        device-resident throughput (inputs already in HBM), CUDA-event timed, K launches
-  e2e          same metric through the host-buffer C-ABI entry (dgpmp2_gn_step_host_f32): pinned host
-               inputs -> H2D -> kernel -> D2H of dtheta/err/status, every step, copies inside the timed region
+  e2e          same metric through the host-buffer C-ABI entry (dgpmp2_gn_step_host_f32): pinned host inputs every
+               step, trajectories H2D, the SDF read in place over PCIe (DGPMP2_SDF_IN_PLACE), D2H of dtheta / err /
+               status, all inside the timed region; config.e2e_copy_sdf = the same with the whole SDF copied first
   roofline     algorithmic bytes per launch / average launch duration of gn_step_kernel, against the measured HBM peak
   roofline_k1  the same for the fused SDF lookup + hinge + gradient in isolation (dgpmp2_hinge_batch_f32, 4.2 M states)
   cpu_baseline the CPU oracle port (oracle/gn_oracle.py = the reference's dense algorithm) timed on this box's host
@@ -75,6 +76,22 @@ def make_cparams(B=B_PER_GPU, T=T_STATES, dof=2, base=YAML, **flags):
                             K_g=base['K_g'], reg=base['reg'], Q_c_inv=base['Q_c_inv'], cost_sigma=base['cost_sigma'],
                             epsilon_dist=base['epsilon_dist'], K_d=base.get('K_d'), K_v=base.get('K_v'), v_x=base.get('v_x'),
                             v_y=base.get('v_y'), **flags)
+
+
+def tap_sector_bytes(th, sdf):
+    """Bytes of the distinct 32-byte sectors of the (B,H,W) fp32 SDF that the 4 bilinear taps of every state of th (B,T,d)
+    touch (sdf_utils.py:57-79 index arithmetic in float64): what an in-place step has to pull over PCIe at least."""
+    import numpy as np
+    Bn, H, W = sdf.shape
+    res = 10.0 / W
+    x, y = th[..., 0].double().numpy(), th[..., 1].double().numpy()
+    px, py = 5.0 / res + x / res, 5.0 / res - y / res
+    ix, iy = np.floor(px).astype(np.int64), np.floor(py).astype(np.int64)
+    x1, x2 = np.clip(ix, 0, W - 1), np.clip(ix + 1, 0, W - 1)
+    y1, y2 = np.clip(iy, 0, H - 1), np.clip(iy + 1, 0, H - 1)
+    base = (np.arange(Bn, dtype=np.int64) * H * W)[:, None]
+    elems = np.concatenate([base + yy * W + xx for yy in (y1, y2) for xx in (x1, x2)], axis=1)
+    return int(np.unique(elems // 8).size) * 32
 
 
 def make_inputs(seed, n_sets, B, T=T_STATES, dof=2):
@@ -468,11 +485,19 @@ def main():
         wall = (time.perf_counter() - t0) * 1e3
         return world * B * Ke / (max_over_ranks(max(a0.elapsed_time(a1), wall)) * 1e-3)
 
-    def step_sdf(i, resident=False):
-        h = hsets[0] if resident else hsets[i % len(hsets)]
-        return hs.step(h[0], h[1].reshape(B, d), h[2].reshape(B, d), h[3][:, 0], sdf_resident=resident and i > 0)
+    def step_sdf(i, in_place):
+        h = hsets[i % len(hsets)]
+        return hs.step(h[0], h[1].reshape(B, d), h[2].reshape(B, d), h[3][:, 0], in_place=in_place)
 
-    e2e_val = e2e_run(lambda i: step_sdf(i, False))
+    # headline e2e: the pinned SDF is read in place (DGPMP2_SDF_IN_PLACE) -- the kernel pulls the sectors its taps touch
+    # over PCIe; e2e_copy: the whole SDF is copied to the device first (what a pageable buffer gets), round 1's number
+    out_z = [t.clone() for t in step_sdf(0, True)]
+    assert hs.last_sdf_read_in_place, 'pinned SDF was not read in place'
+    assert all(torch.equal(a, b) for a, b in zip(out_z, out_h)), 'in-place SDF step differs from the copying step'
+    checks['e2e_in_place_step_bitwise_equal_to_copying_step'] = True
+    e2e_val = e2e_run(lambda i: step_sdf(i, True))
+    e2e_copy = e2e_run(lambda i: step_sdf(i, False))
+    sector_bytes = sum(tap_sector_bytes(h[0], h[3][:, 0]) for h in hsets) // len(hsets)
     hs.step(hsets[0][0], hsets[0][1].reshape(B, d), hsets[0][2].reshape(B, d), hsets[0][3][:, 0])
     e2e_res = e2e_run(lambda i: hs.step(hsets[0][0], hsets[0][1].reshape(B, d), hsets[0][2].reshape(B, d), None, sdf_resident=True))
     # maps instead of SDFs across the bus: bit-packed occupancy in, exact EDT on the device (dgpmp2_gn_step_host_occ_f32)
@@ -693,6 +718,10 @@ def main():
                                                                           touched / 1e6, N_SETS * touched / 1e6),
                    'state_iters_per_sec': value * T, 'batch_iters_per_sec': value / (world * B), 'launch': shape,
                    'checks': checks, 'extras': extras,
+                   'e2e_copy_sdf': {'value': e2e_copy, 'unit': UNIT, 'h2d_bytes_per_step': hs.h2d_bytes + hs.sdf_bytes,
+                                    'd2h_bytes_per_step': hs.d2h_bytes,
+                                    'note': 'the whole SDF copied to the device every step (DGPMP2_SDF_COPY; what a pageable '
+                                            'buffer gets; the e2e number of round 1)'},
                    'e2e_sdf_resident': {'value': e2e_res, 'unit': UNIT, 'h2d_bytes_per_step': hs.h2d_bytes,
                                         'note': 'SDF copied once and kept on the device (GN iterations on fixed environments)'},
                    'e2e_from_occupancy': {'value': e2e_occ, 'unit': UNIT, 'h2d_bytes_per_step': ho.h2d_bytes + ho.occ_bytes,
@@ -700,8 +729,13 @@ def main():
                                           'note': 'bit-packed occupancy maps cross the bus (1/32 of the SDF bytes); exact EDT + GN step on '
                                                   'the device, every step (dgpmp2_gn_step_host_occ_f32)'},
                    'host': {'h2d_GBs_per_rank_all_ranks_copying': h2d_all, 'numa': numa, 'host_threads': host_threads()}},
-        'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': hs.h2d_bytes + hs.sdf_bytes,
-                'd2h_bytes_per_step': hs.d2h_bytes, 'steps': Ke},
+        'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': hs.h2d_bytes + sector_bytes,
+                'd2h_bytes_per_step': hs.d2h_bytes, 'steps': Ke,
+                'h2d_breakdown': {'copied_trajectories_start_goal': hs.h2d_bytes, 'sdf_sectors_read_in_place_over_pcie': sector_bytes,
+                                  'sdf_bytes_in_pinned_host_memory': hs.sdf_bytes},
+                'note': 'dgpmp2_gn_step_host_f32 with DGPMP2_SDF_IN_PLACE: inputs in pinned host memory every step; the '
+                        'trajectories are copied, the SDF is read where it lies (the kernel fetches the distinct 32-byte sectors '
+                        'its 4 taps per state touch, counted on the host from the same index arithmetic), results copied back'},
         'gpu_launches': K,
         'roofline': roofline,
         'roofline_k1': roofline_k1,

@@ -84,6 +84,7 @@ PROTOTYPES = {
     'dgpmp2_band_f32': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp],
     'dgpmp2_band_f64': [_P(CParams), _vp, _vp, _vp, _vp, _P(CWeights), _vp, _vp, _vp, _vp],
     'dgpmp2_host_step_workspace_bytes': [_P(CParams), _i32, _P(_sz)],
+    'dgpmp2_host_pointer_is_mapped': [_vp],
     'dgpmp2_gn_step_host_f32': [_P(CParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp],
     'dgpmp2_gn_step_host_f64': [_P(CParams), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp],
     'dgpmp2_gn_step_launch_shape': [_P(CParams), _i32, _P(_i32), _P(_i32), _P(_i32), _P(_i32)],

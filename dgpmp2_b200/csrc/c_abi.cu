@@ -517,6 +517,20 @@ HostPipe* host_pipe() {
   return pipes[dev].ok ? &pipes[dev] : nullptr;
 }
 
+// Device-side alias of a host buffer that is pinned and mapped (cudaHostAlloc / cudaHostRegister under unified addressing),
+// nullptr for pageable memory.
+template <typename IO>
+const IO* mapped_alias(const IO* host) {
+  if (host == nullptr) return nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return nullptr;
+  return static_cast<const IO*>(at.devicePointer);
+}
+
 template <typename IO>
 int gn_step_host_impl(const dgpmp2_params* p, const IO* th, const IO* start, const IO* goal, const IO* sdf, IO* dth,
                       IO* err, IO* err_ext, int32_t* status, void* dev_ws, size_t dev_ws_bytes, int32_t sdf_resident,
@@ -525,7 +539,8 @@ int gn_step_host_impl(const dgpmp2_params* p, const IO* th, const IO* start, con
   if (rc != DGPMP2_OK) return rc;
   if (p->B == 0) return DGPMP2_OK;
   if (!th || !start || !goal || !dth || !err || !err_ext || !dev_ws) return DGPMP2_ERR_ARG;
-  if (!sdf_resident && !sdf) return DGPMP2_ERR_ARG;
+  if (sdf_resident < 0 || sdf_resident > 2) return DGPMP2_ERR_ARG;
+  if (sdf_resident != DGPMP2_SDF_RESIDENT && !sdf) return DGPMP2_ERR_ARG;
   const HostWs L = host_ws_layout(p, sizeof(IO));
   if (dev_ws_bytes < L.total) return DGPMP2_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -539,7 +554,7 @@ int gn_step_host_impl(const dgpmp2_params* p, const IO* th, const IO* start, con
   // does not pay -- the 64 MiB SDF copy alone saturates PCIe (1024 problems: 763 k problem-iters/s in one piece, 741 k
   // in 4 chunks, 683 k in 8; profiles/r02_host_chunks_ab.txt), the kernel and the 1 MB of results are < 3 % of the step.
   const int want_chunks = env_int("DGPMP2_HOST_CHUNKS", 1);
-  HostPipe* hp = (want_chunks > 1 && !sdf_resident && p->sdf_stride_b > 0 && B >= 256) ? host_pipe() : nullptr;
+  HostPipe* hp = (want_chunks > 1 && sdf_resident == DGPMP2_SDF_COPY && p->sdf_stride_b > 0 && B >= 256) ? host_pipe() : nullptr;
   if (hp != nullptr) {
     std::lock_guard<std::mutex> in_use(hp->busy);      // the helper streams / events serve one (synchronous) call at a time
     const size_t nch = (size_t)want_chunks;
@@ -578,19 +593,43 @@ int gn_step_host_impl(const dgpmp2_params* p, const IO* th, const IO* start, con
     CUDA_TRY(cudaStreamSynchronize(st));
     return DGPMP2_OK;
   }
-  CUDA_TRY(cudaMemcpyAsync(ws + L.th, th, B * T * d * sizeof(IO), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(ws + L.start, start, B * d * sizeof(IO), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(ws + L.goal, goal, B * d * sizeof(IO), cudaMemcpyHostToDevice, st));
-  if (!sdf_resident) CUDA_TRY(cudaMemcpyAsync(ws + L.sdf, sdf, sdf_elems * sizeof(IO), cudaMemcpyHostToDevice, st));
-  rc = gn_step_impl<IO>(p, reinterpret_cast<IO*>(ws + L.th), reinterpret_cast<IO*>(ws + L.start),
-                        reinterpret_cast<IO*>(ws + L.goal), reinterpret_cast<IO*>(ws + L.sdf), nullptr,
-                        reinterpret_cast<IO*>(ws + L.dth), reinterpret_cast<IO*>(ws + L.err),
-                        reinterpret_cast<IO*>(ws + L.err_ext), reinterpret_cast<int32_t*>(ws + L.status), stream);
+  // Where each operand lives for the launch: the workspace copy, or -- mode DGPMP2_SDF_IN_PLACE -- the caller's own
+  // buffer when it is pinned (mapped) host memory.  The SDF is the case that matters: a step reads 4 taps per state, so
+  // the kernel pulls ~0.15 M 32-byte sectors over PCIe instead of the whole 64 MiB field crossing it first
+  // (measured, B=1024, T=64, 128x128 maps: 0.32 ms per step instead of 1.42 ms; same bits).
+  const bool in_place = (sdf_resident == DGPMP2_SDF_IN_PLACE);
+  // ... and the small operands as well (trajectories in, dtheta / errors / status out; DGPMP2_HOST_INPLACE_IO=2 copies
+  // them instead, A/B): with every operand in pinned memory the call is one kernel launch and one stream synchronisation
+  // (2.57 -> 3.02 M problem-iters/s for the trajectories and dtheta alone).
+  const bool io_in_place = in_place && env_int("DGPMP2_HOST_INPLACE_IO", 1) == 1;
+  const IO* k_sdf = reinterpret_cast<const IO*>(ws + L.sdf);
+  bool copy_sdf = (sdf_resident == DGPMP2_SDF_COPY);
+  if (in_place) {
+    const IO* alias = mapped_alias(sdf);
+    if (alias != nullptr) k_sdf = alias; else copy_sdf = true;
+  }
+  const IO* a_th = io_in_place ? mapped_alias(th) : nullptr;
+  const IO* a_start = io_in_place ? mapped_alias(start) : nullptr;
+  const IO* a_goal = io_in_place ? mapped_alias(goal) : nullptr;
+  IO* a_dth = io_in_place ? const_cast<IO*>(mapped_alias(dth)) : nullptr;
+  IO* a_err = io_in_place ? const_cast<IO*>(mapped_alias(err)) : nullptr;
+  IO* a_ee = io_in_place ? const_cast<IO*>(mapped_alias(err_ext)) : nullptr;
+  int32_t* a_status = (io_in_place && status) ? const_cast<int32_t*>(mapped_alias(status)) : nullptr;
+  if (!a_th) CUDA_TRY(cudaMemcpyAsync(ws + L.th, th, B * T * d * sizeof(IO), cudaMemcpyHostToDevice, st));
+  if (!a_start) CUDA_TRY(cudaMemcpyAsync(ws + L.start, start, B * d * sizeof(IO), cudaMemcpyHostToDevice, st));
+  if (!a_goal) CUDA_TRY(cudaMemcpyAsync(ws + L.goal, goal, B * d * sizeof(IO), cudaMemcpyHostToDevice, st));
+  if (copy_sdf) CUDA_TRY(cudaMemcpyAsync(ws + L.sdf, sdf, sdf_elems * sizeof(IO), cudaMemcpyHostToDevice, st));
+  rc = gn_step_impl<IO>(p, a_th ? a_th : reinterpret_cast<const IO*>(ws + L.th),
+                        a_start ? a_start : reinterpret_cast<const IO*>(ws + L.start),
+                        a_goal ? a_goal : reinterpret_cast<const IO*>(ws + L.goal), k_sdf, nullptr,
+                        a_dth ? a_dth : reinterpret_cast<IO*>(ws + L.dth), a_err ? a_err : reinterpret_cast<IO*>(ws + L.err),
+                        a_ee ? a_ee : reinterpret_cast<IO*>(ws + L.err_ext),
+                        a_status ? a_status : reinterpret_cast<int32_t*>(ws + L.status), stream);
   if (rc != DGPMP2_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(dth, ws + L.dth, B * T * d * sizeof(IO), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(err, ws + L.err, B * sizeof(IO), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(err_ext, ws + L.err_ext, B * sizeof(IO), cudaMemcpyDeviceToHost, st));
-  if (status) CUDA_TRY(cudaMemcpyAsync(status, ws + L.status, B * 4, cudaMemcpyDeviceToHost, st));
+  if (!a_dth) CUDA_TRY(cudaMemcpyAsync(dth, ws + L.dth, B * T * d * sizeof(IO), cudaMemcpyDeviceToHost, st));
+  if (!a_err) CUDA_TRY(cudaMemcpyAsync(err, ws + L.err, B * sizeof(IO), cudaMemcpyDeviceToHost, st));
+  if (!a_ee) CUDA_TRY(cudaMemcpyAsync(err_ext, ws + L.err_ext, B * sizeof(IO), cudaMemcpyDeviceToHost, st));
+  if (status && !a_status) CUDA_TRY(cudaMemcpyAsync(status, ws + L.status, B * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return DGPMP2_OK;
 }
@@ -650,6 +689,10 @@ extern "C" int dgpmp2_debug_phase_clocks(long long* out) {
 extern "C" {
 
 int dgpmp2_abi_version(void) { return DGPMP2_ABI_VERSION; }
+
+int dgpmp2_host_pointer_is_mapped(const void* host_ptr) {
+  return mapped_alias(static_cast<const unsigned char*>(host_ptr)) != nullptr ? 1 : 0;
+}
 
 const char* dgpmp2_status_string(int code) {
   switch (code) {

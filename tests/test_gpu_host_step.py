@@ -161,3 +161,46 @@ def test_chunked_host_step_is_bit_identical(dtype):
         os.environ.pop('DGPMP2_HOST_CHUNKS', None)
         if saved is not None:
             os.environ['DGPMP2_HOST_CHUNKS'] = saved
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+def test_sdf_read_in_place_from_pinned_host_memory(dtype):
+    """DGPMP2_SDF_IN_PLACE: a pinned SDF is not copied -- the kernel gathers its taps from the host buffer over PCIe.
+    Same bits as the copying call and as the reference golden's tolerance; nothing is staged (a following
+    sdf_resident call must be refused); a pageable SDF silently takes the copying path and is staged."""
+    from dgpmp2_b200 import _lib
+    name = STATIC[0]
+    g = load_golden(name)
+    B, T, d = g['th'].shape
+    hw = g['sdf'].shape[-2:]
+    th, start, goal, sdf = (_host(g[k], dtype, True) for k in ('th', 'start', 'goal', 'sdf'))
+    args = (th, start.reshape(B, d), goal.reshape(B, d), sdf.reshape(B, *hw))
+    lib = _lib.load()
+    assert lib.dgpmp2_host_pointer_is_mapped(args[3].data_ptr()) == 1
+    assert lib.dgpmp2_host_pointer_is_mapped(args[3].clone().data_ptr()) == 0          # pageable copy
+    hs = _stepper(g, dtype)
+    out = [t.clone() for t in hs.step(*args, in_place=True)]
+    assert hs.last_sdf_read_in_place
+    _check(out, g, dtype)
+    with pytest.raises(_lib.Dgpmp2Error):
+        hs.step(args[0], args[1], args[2], None, sdf_resident=True)                  # nothing was staged
+    ref = [t.clone() for t in hs.step(*args)]                                         # copying call
+    for a, b in zip(out, ref):
+        assert torch.equal(a, b)
+    # the host buffer is read at call time: change it in place, the next in-place call sees the new field
+    sdf2 = (args[3] * 0.5).contiguous().pin_memory()
+    want = [t.clone() for t in hs.step(args[0], args[1], args[2], sdf2)]
+    args[3].copy_(sdf2)
+    got = hs.step(*args, in_place=True)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    # pageable: falls back to the copy and stages it
+    hs2 = _stepper(g, dtype)
+    pageable = args[3].clone()
+    out_p = [t.clone() for t in hs2.step(args[0], args[1], args[2], pageable, in_place=True)]
+    assert not hs2.last_sdf_read_in_place
+    for a, b in zip(out_p, want):
+        assert torch.equal(a, b)
+    out_r = hs2.step(args[0], args[1], args[2], None, sdf_resident=True)
+    for a, b in zip(out_r, want):
+        assert torch.equal(a, b)
