@@ -302,8 +302,8 @@ int dgpmp2_band_f64(const dgpmp2_params* p, const double* th, const double* star
  *                            whole field being copied first (B=1024, T=64, 128x128 fp32 maps on B200: 0.32 ms per step
  *                            instead of 1.42 ms, same bits).  Nothing is staged: the workspace SDF is left as it was.
  *                            Pageable `sdf`: falls back to DGPMP2_SDF_COPY.  The right mode for an SDF used once.
- *                            In this mode th / start / goal / dth / err / err_ext / status that are pinned are likewise
- *                            read and written in place by the kernel (no copies at all: one launch + one synchronise).
+ * In every mode those of th / start / goal / dth / err / err_ext / status that are pinned (mapped) host memory are read
+ * and written in place by the kernel instead of being copied (results are the same bits either way).
  * Opt-in (environment DGPMP2_HOST_CHUNKS=n > 1, per-problem SDFs, B >= 256): the batch is processed in n chunks that
  * alternate between two library-owned helper streams (created once per device, the only process-wide state of the
  * library; calls are serialised on them), so that one chunk's kernel and device-to-host copies overlap the next
