@@ -25,7 +25,7 @@ int cuda_fail(cudaError_t e) {
 }
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_); } while (0)
 
-constexpr int kPdlDefault = 1;       // DGPMP2_PDL: 1 = plain launches (default), 2 = programmatic dependent launch of gn_step
+constexpr int kPdlDefault = 2;       // DGPMP2_PDL: 1 = plain launches, 2 = programmatic dependent launch of gn_step (default)
 constexpr int kSmemLimit = 232448;   // 227 KB opt-in dynamic shared memory per CTA on sm_100
 constexpr int kMpSmemLimit = kSmemLimit - 2048;   // gn_step_mp_kernel also holds ~1.2 KB of static shared memory
 
