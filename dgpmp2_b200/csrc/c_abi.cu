@@ -79,6 +79,7 @@ int choose_shape(int B, int T, int mode, LaunchShape& s, bool balanced = false) 
   if (np > B) np = B;
   if (np < 1) np = 1;
   while (np > 1 && StepSmem<D, IO>::bytes(np, T, mode) > (size_t)kSmemLimit) --np;
+  if (balanced) { const int cap = env_int("DGPMP2_NP_MAX", np); if (cap < np) np = cap; }   // experiment: several smaller co-resident CTAs per SM
   int big_waves = -1;                            // -1: every CTA takes np problems
   if (balanced && np < q && env_int("DGPMP2_BALANCED", 1) == 1 && getenv("DGPMP2_NP") == nullptr) {
     const int w = (q + np - 1) / np;
