@@ -693,9 +693,11 @@ def main():
                        'states': k1['states'], 'kernel_us': k1['us'], 'algorithmic_bytes_per_launch': alg1,
                        'achieved': a1g, 'peak': peak, 'unit': 'GB/s', 'frac': a1g / peak,
                        'traffic': prof.get('k1_dram_bytes_per_launch'), 'traffic_source': prof.get('k1_source'),
-                       'note': '36 B per state = 8 B position + four 4-byte taps + 12 B out; a 2x2 tap patch costs 2 rows x 1-2 '
-                               '32-byte DRAM sectors (measured 39 B per state), so >= 59 B per state must cross HBM: the '
-                               'algorithmic fraction is capped near 0.6 x the achievable DRAM efficiency (DESIGN.md 4.5)'}
+                       'note': '36 B per state = 8 B position + four 4-byte taps + 12 B out.  A load that misses L2 fetches a whole '
+                               '128-byte line from DRAM on B200 (scratch/ubench8.cu, profiles/r02_ubench8_fetch_granularity.txt); the '
+                               'distinct-line footprint of the taps is 39.5 B per state on this workload (= the ncu figure: no '
+                               're-reads), so >= 59.5 B per state must cross HBM and the algorithmic fraction is capped at 0.605 x '
+                               'the DRAM efficiency reached (DESIGN.md 4.5)'}
 
     # ---------------- CPU baseline (oracle port of the reference algorithm) ----------------
     cpu = None

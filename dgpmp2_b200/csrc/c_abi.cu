@@ -445,7 +445,7 @@ int hinge_batch_impl(const IO* sdf, int32_t B, int32_t H, int32_t W, int64_t sdf
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const double ox = 0.0 - x_lo / res, oy = 0.0 - y_lo / res;
   const long long n = (long long)B * N;
-  const long long blocks = (n + 511) / 512;
+  const long long blocks = (n + 256 * DGPMP2_K1_NPT - 1) / (256 * DGPMP2_K1_NPT);
   if (blocks > 0x7fffffffLL) return DGPMP2_ERR_UNSUPPORTED;
   hinge_kernel<IO><<<(unsigned)blocks, 256, 0, st>>>(sdf, B, H, W, sdf_sb, pts, N, res, 1.0 / res, ox, oy, eps, eps_sb, eps_sn,
                                                      eps_const, r_sphere, cost, He);

@@ -900,43 +900,71 @@ obstacle_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
 // gradient out -- the fused SDF bilinear lookup + obstacle cost + Jacobian in its leanest form: per point 8 B of
 // position, four 4-byte taps, 4 + 8 B of output = the 36 algorithmic bytes of SURVEY 8(d).  Two consecutive points per
 // thread: one 16-byte load of both positions, one 8-byte store of both costs, one 16-byte store of both gradients
-// (fp32 I/O), eight independent tap loads in flight.  HBM-bound; what it can reach is set by the 32-byte DRAM sector:
-// a 2 x 2 tap patch touches 2 rows x (1..2) sectors, shared with the neighbouring states of the same trajectory only.
+// (fp32 I/O), eight independent tap loads in flight.  HBM-bound; what it can reach is set by the DRAM fetch granularity,
+// which is a whole 128-byte line per miss on B200 whatever the load flavour (scratch/ubench8.cu): a 2 x 2 tap patch
+// touches 2 image rows = 2 lines, shared with the neighbouring states of the same trajectory only.
 // ---------------------------------------------------------------------------
+#ifndef DGPMP2_K1_MINBLOCKS
+#define DGPMP2_K1_MINBLOCKS 6     // <= 40 registers: 6 CTAs = 48 warps per SM (measured 50.3 -> 46.9 us against 44 registers / 5 CTAs)
+#endif
+#ifndef DGPMP2_K1_PFDIST
+#define DGPMP2_K1_PFDIST 1
+#endif
+#ifndef DGPMP2_K1_NPT
+#define DGPMP2_K1_NPT 2           // consecutive points per thread (even; 4 measured slower: 53-55 us)
+#endif
 template <typename IO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, DGPMP2_K1_MINBLOCKS)
 hinge_kernel(const IO* __restrict__ sdf, int B, int H, int W, long long sdf_sb, const IO* __restrict__ pts, int N,
              double res, double inv_res, double orig_x, double orig_y, const IO* __restrict__ eps, long long e_sb,
              long long e_sn, double eps_const, double r_sphere, IO* __restrict__ cost, IO* __restrict__ He) {
   using V2 = typename Vec2<IO>::type;
+  constexpr int NPT = DGPMP2_K1_NPT;
   const long long n = (long long)B * N;
-  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * NPT;
   if (i0 >= n) return;
-  const bool two = (i0 + 1 < n);
-  V2 p[2];
-  p[0] = __ldg(reinterpret_cast<const V2*>(pts) + i0);
-  p[1] = two ? __ldg(reinterpret_cast<const V2*>(pts) + i0 + 1) : p[0];
-  ObsTerm ob[2];
+  const int cnt = (int)((n - i0 < NPT) ? (n - i0) : NPT);
+#if DGPMP2_K1_PFDIST > 0
+  {  // L2 prefetch of the positions a CTA DGPMP2_K1_PFDIST waves of resident CTAs later will read (one request per 128-byte
+     // line): the first of a thread's two dependent DRAM round trips then hits L2 (measured 47.0 -> 45.0 us; prefetching the
+     // tap rows of later CTAs the same way was slower, 51-61 us)
+    const long long ip = i0 + (long long)DGPMP2_K1_PFDIST * 148 * DGPMP2_K1_MINBLOCKS * 256 * NPT;
+    if (ip < n && (threadIdx.x & (128 / (NPT * 2 * (int)sizeof(IO)) - 1)) == 0)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const V2*>(pts) + ip));
+  }
+#endif
+  V2 p[NPT];
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const long long i = i0 + (two ? k : 0);
-    const int b = (int)(i / N), j = (int)(i - (long long)b * N);
+  for (int k = 0; k < NPT; ++k) p[k] = __ldg(reinterpret_cast<const V2*>(pts) + i0 + ((k < cnt) ? k : 0));
+  ObsTerm ob[NPT];
+#pragma unroll
+  for (int k = 0; k < NPT; ++k) {
+    const long long i = i0 + ((k < cnt) ? k : 0);
+    // the point's trajectory: 32-bit division when the point count allows it
+    const int b = (n <= 0xffffffffLL) ? (int)((unsigned)i / (unsigned)N) : (int)(i / N);
+    const int j = (int)(i - (long long)b * N);
     const double e = (eps != nullptr) ? ldg_d(eps + (long long)b * e_sb + (long long)j * e_sn) : eps_const;
     const SdfSample sm = sdf_bilinear<IO, false>(sdf + (size_t)b * sdf_sb, H, W, orig_x, orig_y, res, (double)p[k].x,
                                                  (double)p[k].y, inv_res);
     ob[k] = hinge(sm, __dadd_rn(e, r_sphere));
   }
-  if (two && ((reinterpret_cast<unsigned long long>(cost) | (reinterpret_cast<unsigned long long>(He) >> 1)) & (2 * sizeof(IO) - 1)) == 0) {
-    V2 c; c.x = (IO)ob[0].c; c.y = (IO)ob[1].c;
-    *reinterpret_cast<V2*>(cost + i0) = c;                 // i0 is even: 2-element aligned when the base is
-    V2 h0, h1; h0.x = (IO)ob[0].hx; h0.y = (IO)ob[0].hy; h1.x = (IO)ob[1].hx; h1.y = (IO)ob[1].hy;
-    reinterpret_cast<V2*>(He)[i0] = h0;
-    reinterpret_cast<V2*>(He)[i0 + 1] = h1;
+  if (cnt == NPT && ((reinterpret_cast<unsigned long long>(cost) | (reinterpret_cast<unsigned long long>(He) >> 1)) & (2 * sizeof(IO) - 1)) == 0) {
+#pragma unroll
+    for (int k = 0; k < NPT; k += 2) {
+      V2 c; c.x = (IO)ob[k].c; c.y = (IO)ob[k + 1].c;
+      *reinterpret_cast<V2*>(cost + i0 + k) = c;             // i0 + k is even: 2-element aligned when the base is
+      V2 h0, h1; h0.x = (IO)ob[k].hx; h0.y = (IO)ob[k].hy; h1.x = (IO)ob[k + 1].hx; h1.y = (IO)ob[k + 1].hy;
+      reinterpret_cast<V2*>(He)[i0 + k] = h0;
+      reinterpret_cast<V2*>(He)[i0 + k + 1] = h1;
+    }
   } else {
-    for (int k = 0; k < (two ? 2 : 1); ++k) {
-      cost[i0 + k] = (IO)ob[k].c;
-      He[2 * (i0 + k)] = (IO)ob[k].hx;
-      He[2 * (i0 + k) + 1] = (IO)ob[k].hy;
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {      // (unrolled: a dynamic index would put ob[] in local memory)
+      if (k < cnt) {
+        cost[i0 + k] = (IO)ob[k].c;
+        He[2 * (i0 + k)] = (IO)ob[k].hx;
+        He[2 * (i0 + k) + 1] = (IO)ob[k].hy;
+      }
     }
   }
 }
