@@ -30,10 +30,16 @@ def is_stale():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
+LAST_ACTION = None     # 'compiled' or 'reused' after build()
+
+
 def build(force=False, verbose=False):
     """Compile the CUDA library if missing or older than its sources. Returns the .so path."""
+    global LAST_ACTION
     if not force and not is_stale():
+        LAST_ACTION = 'reused'
         return LIB_PATH
+    LAST_ACTION = 'compiled'
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + \
           [os.path.join(CSRC, s) for s in SOURCES]
