@@ -315,8 +315,8 @@ int gn_step_backward_impl(const dgpmp2_params* p, const IO* th, const IO* start,
   if (!th || !start || !goal || !sdf || !dth || !g_dth) return DGPMP2_ERR_ARG;
   KParams k = make_kparams(p);
   const KWeights<IO> kw = make_kweights<IO>(w);
-  finish_kparams(k, kw);
-  k.static_gp = 0;   // the backward evaluates the GP blocks generically (it needs Q^-1 itself)
+  finish_kparams(k, kw);   // static-GP blocks + fused level 1 for the band assembly, as in the forward step
+  if (env_int("DGPMP2_BWD_STATIC", 1) != 1) { k.static_gp = 0; k.fuse1 = 0; }   // A/B: the generic assembly of round 1
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p->dof == 2)
     return launch_bwd<2, IO>(k, kw, th, start, goal, sdf, dth, g_dth, g_err_ext, g_th, g_start, g_goal, g_qc, g_w, g_eps,

@@ -65,7 +65,8 @@ template <int DOF, typename IO>
 __device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO>& Wt, const StepSmem<2 * DOF, IO>& S,
                                              int b0, int np,
                                              const IO* __restrict__ start, const IO* __restrict__ goal,
-                                             const IO* __restrict__ sdf, bool fuse1 = false, bool prefetch = true) {
+                                             const IO* __restrict__ sdf, bool fuse1 = false, bool prefetch = true,
+                                             const IO* __restrict__ rhs = nullptr) {
   constexpr int D = 2 * DOF;
   using N = Node<D>;
   const int T = P.T;
@@ -98,6 +99,11 @@ __device__ __forceinline__ void assemble_cta(const KParams& P, const KWeights<IO
     NodeOut<DOF> o;
     assemble_node<DOF, IO>(P, Wt, b, t, thp, thc, thn, start + (size_t)b * D, goal + (size_t)b * D,
                            sdf + (size_t)b * P.sdf_sb, o);
+    if (rhs != nullptr) {                          // backward kernel: the system is solved for a given right-hand side
+      const IO* gp = rhs + ((size_t)b * T + t) * D;
+#pragma unroll
+      for (int a = 0; a < D; ++a) o.r[a] = ldg_d(gp + a);
+    }
     double* nd = S.nodes + (size_t)p * N::problem_stride(T) + (size_t)slot * N::kStride;
     if (fuse1 && slot < P.plan.lv[0].ne) {          // level-1 node: the slots [0, ne) of level order
       constexpr int DS = N::DS;
@@ -530,23 +536,13 @@ gn_step_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict_
   }
   __syncthreads();
 
-  assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf);
-  __syncthreads();
-  {  // right-hand side := gbar (slot order)
-    const float inv_T = P.plan.inv_T;
-    for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
-      const int p = fast_div(m, inv_T), slot = m - p * T;
-      const int t = bcr_state_of_slot(T, slot);
-      const IO* gp = g_dth + ((size_t)(b0 + p) * T + t) * D;
-      double v[D];
-#pragma unroll
-      for (int a = 0; a < D; ++a) v[a] = ldg_d(gp + a);
-      st_vec<D>(S.nodes + (size_t)p * N::problem_stride(T) + (size_t)slot * N::kStride + N::oR, v);
-    }
-  }
+  // the band of the forward step with gbar as its right-hand side (static-GP blocks and the level-1 elimination fused
+  // into the assembly exactly as in gn_step_kernel; backward_node below evaluates Q^-1 itself)
+  const bool fuse1 = P.fuse1 != 0;
+  assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf, fuse1, true, g_dth);
   __syncthreads();
 
-  bcr_solve<D>(S.nodes, P.plan, T, np, S.fail);   // lambda in every record's [oR, oR+D)
+  bcr_solve<D>(S.nodes, P.plan, T, np, S.fail, fuse1);   // lambda in every record's [oR, oR+D)
 
   const double invM = 1.0 / (double)P.M;
   const float inv_T = P.plan.inv_T;
