@@ -249,6 +249,26 @@ __device__ __forceinline__ void step_epilogue(const KParams& P, const StepSmem<2
     for (int p = threadIdx.x; p < np; p += blockDim.x) status[b0 + p] = S.fail[p];
 }
 
+// Early SDF prefetch (measured DRAM-cold, B=1024: 19.16 -> 18.21 us at T=64, 38.0 -> 36.4 us at T=128): every thread reads
+// the position of one state straight from global memory (natural order, coalesced; the staging loads that follow then
+// hit L1 / L2) and requests the two SDF rows of its obstacle factor before the trajectory is staged, so the DRAM-cold
+// gather starts one barrier earlier.  A hint only: the pixel is located in float arithmetic.
+template <int D, typename IO>
+__device__ __forceinline__ void early_sdf_prefetch(const KParams& P, int T, int b0, int np, const IO* __restrict__ th,
+                                                   const IO* __restrict__ sdf) {
+  const IO* src = th + (size_t)b0 * T * D;
+  const float inv_T = P.plan.inv_T;
+  for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
+    const int p = fast_div(m, inv_T);
+    const float fx = (float)P.orig_x + (float)__ldg(src + (size_t)m * D) * (float)P.inv_res;
+    const float fy = (float)P.orig_y - (float)__ldg(src + (size_t)m * D + 1) * (float)P.inv_res;
+    const int ix = min(max(__float2int_rd(fx), 0), P.W - 1), iy = min(max(__float2int_rd(fy), 0), P.H - 1);
+    const IO* q = sdf + (size_t)(b0 + p) * P.sdf_sb + (size_t)iy * P.W + ix;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q + ((iy + 1 < P.H) ? P.W : 0)));
+  }
+}
+
 // One fused Gauss-Newton iteration.  grid = ceil(B / NP), block = NP * TPP threads (rounded to a warp).
 template <int DOF, typename IO>
 __global__ void __launch_bounds__(DOF == 2 ? 512 : 256)
@@ -274,22 +294,7 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
   DGPMP2_STAMP(0);
 
   const bool early = (P.prefetch & 2) != 0;
-  if (early) {
-    // Early SDF prefetch (measured DRAM-cold, B=1024: 19.16 -> 18.21 us at T=64, 38.0 -> 36.4 us at T=128): every thread reads the position of one state straight from
-    // global memory (natural order, coalesced; the staging loads below then hit L1 / L2) and requests the two SDF rows of
-    // its obstacle factor before the trajectory is staged, so the DRAM-cold gather starts one barrier earlier.
-    const IO* src = th + (size_t)b0 * T * D;
-    const float inv_T = P.plan.inv_T;
-    for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
-      const int p = fast_div(m, inv_T);
-      const float fx = (float)P.orig_x + (float)__ldg(src + (size_t)m * D) * (float)P.inv_res;
-      const float fy = (float)P.orig_y - (float)__ldg(src + (size_t)m * D + 1) * (float)P.inv_res;
-      const int ix = min(max(__float2int_rd(fx), 0), P.W - 1), iy = min(max(__float2int_rd(fy), 0), P.H - 1);
-      const IO* q = sdf + (size_t)(b0 + p) * P.sdf_sb + (size_t)iy * P.W + ix;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(q + ((iy + 1 < P.H) ? P.W : 0)));
-    }
-  }
+  if (early) early_sdf_prefetch<D, IO>(P, T, b0, np, th, sdf);
   cta_prologue<D, IO>(P, S, T, NP, np, th + (size_t)b0 * T * D, false);
   __syncthreads();
   DGPMP2_STAMP(1);
@@ -528,6 +533,8 @@ gn_step_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict_
   const int b0 = blockIdx.x * NP;
   const int np = min(NP, P.B - b0);
 
+  const bool early = (P.prefetch & 2) != 0;
+  if (early) early_sdf_prefetch<D, IO>(P, T, b0, np, th, sdf);
   cta_prologue<D, IO>(P, S, T, NP, np, th + (size_t)b0 * T * D, false);
   {
     const IO* src = dth + (size_t)b0 * T * D;
@@ -539,7 +546,7 @@ gn_step_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict_
   // the band of the forward step with gbar as its right-hand side (static-GP blocks and the level-1 elimination fused
   // into the assembly exactly as in gn_step_kernel; backward_node below evaluates Q^-1 itself)
   const bool fuse1 = P.fuse1 != 0;
-  assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf, fuse1, true, g_dth);
+  assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf, fuse1, !early, g_dth);
   __syncthreads();
 
   bcr_solve<D>(S.nodes, P.plan, T, np, S.fail, fuse1);   // lambda in every record's [oR, oR+D)
