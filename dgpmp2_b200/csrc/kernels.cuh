@@ -445,10 +445,12 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
   cta_prologue<D, IO>(P, S, T, NP, np, th_init + (size_t)b0 * T * D, true);
   __syncthreads();
   const double invM = 1.0 / (double)P.M;
+  const bool fuse1 = P.fuse1 != 0;      // uniform (host: static GP blocks and at least one elimination level)
 
   for (int j = 0;; ++j) {
-    // assemble at the current iterate; the errors at iterate j are a by-product
-    assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf);
+    // assemble at the current iterate (level-1 elimination fused in, as in gn_step_kernel); the errors at iterate j
+    // are a by-product
+    assemble_cta<DOF, IO>(P, Wt, S, b0, np, start, goal, sdf, fuse1);
     __syncthreads();
     const bool last = (j >= max_iters);
     reduce2_per_problem(S.nodes + N::oX, N::kStride, N::problem_stride(T), np, T, [&](int p, double s0, double s1) {
@@ -470,7 +472,7 @@ gn_solve_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ t
     for (int p = 0; p < np; ++p) all_done = all_done && (done[p] == 2);
     if (all_done || last) break;
 
-    bcr_solve<D>(S.nodes, P.plan, T, np, S.fail);
+    bcr_solve<D>(S.nodes, P.plan, T, np, S.fail, fuse1);
 
     // th <- th + dth for problems still running; |dth|^2 partials
     for (int m = threadIdx.x; m < np * T; m += blockDim.x) {

@@ -226,3 +226,34 @@ def test_slot_maps_closed_forms_are_inverse_bijections():
             assert state_of_slot_closed_form(T, m) == t_ == state_of_slot(off, nlev, T, m)
             seen.add(m)
         assert len(seen) == T
+
+
+def test_launch_shape_query_balanced_cta_sizes():
+    """dgpmp2_gn_step_launch_shape needs no GPU (148 SMs assumed without a device): one CTA per SM when the SM's share
+    fits (B=1024, T=64: 7 problems x 147 CTAs); two CTA sizes when it does not (T=128: 4 problems of 55 KB per CTA ->
+    148 x 4 + 144 x 3 = 292 CTAs instead of 256 x 4 in ragged waves); DGPMP2_BALANCED=2 gives the uniform grid."""
+    import os
+    from dgpmp2_b200 import _lib, ops
+    from tests.helpers import YAML
+    if torch.cuda.is_available():
+        pytest.skip('the shapes below assume the 148-SM default used when no device is present')
+
+    def shape(B, T):
+        cp = _lib.make_params(B=B, T=T, dof=2, H=128, W=128, x_lims=(-5.0, 5.0), y_lims=(-5.0, 5.0), total_time_sec=10.0,
+                              r_sphere=0.4, K_s=YAML['K_s'], K_g=YAML['K_g'], reg=YAML['reg'], Q_c_inv=YAML['Q_c_inv'],
+                              cost_sigma=YAML['cost_sigma'], epsilon_dist=YAML['epsilon_dist'])
+        return ops.launch_shape(cp)
+    saved = os.environ.pop('DGPMP2_BALANCED', None)
+    try:
+        s = shape(1024, 64)
+        assert (s['problems_per_cta'], s['grid'], s['threads']) == (7, 147, 448)
+        s = shape(1024, 128)
+        assert (s['problems_per_cta'], s['grid']) == (4, 292) and s['smem_bytes'] <= 232448
+        assert 148 * 4 + (292 - 148) * 3 >= 1024 > 148 * 4 + (291 - 148) * 3
+        os.environ['DGPMP2_BALANCED'] = '2'
+        s = shape(1024, 128)
+        assert (s['problems_per_cta'], s['grid']) == (4, 256)
+    finally:
+        os.environ.pop('DGPMP2_BALANCED', None)
+        if saved is not None:
+            os.environ['DGPMP2_BALANCED'] = saved
