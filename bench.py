@@ -78,9 +78,10 @@ def make_cparams(B=B_PER_GPU, T=T_STATES, dof=2, base=YAML, **flags):
                             v_y=base.get('v_y'), **flags)
 
 
-def tap_sector_bytes(th, sdf):
-    """Bytes of the distinct 32-byte sectors of the (B,H,W) fp32 SDF that the 4 bilinear taps of every state of th (B,T,d)
-    touch (sdf_utils.py:57-79 index arithmetic in float64): what an in-place step has to pull over PCIe at least."""
+def tap_sector_bytes(th, sdf, granule_bytes=128):
+    """Bytes of the distinct `granule_bytes`-sized, aligned pieces of the (B,H,W) fp32 SDF that the 4 bilinear taps of every
+    state of th (B,T,d) touch (sdf_utils.py:57-79 index arithmetic in float64): what an in-place step pulls over PCIe.
+    128 bytes = the line a B200 load miss fetches (scratch/ubench8.cu); 32 bytes = the sector, a lower bound."""
     import numpy as np
     Bn, H, W = sdf.shape
     res = 10.0 / W
@@ -91,7 +92,8 @@ def tap_sector_bytes(th, sdf):
     y1, y2 = np.clip(iy, 0, H - 1), np.clip(iy + 1, 0, H - 1)
     base = (np.arange(Bn, dtype=np.int64) * H * W)[:, None]
     elems = np.concatenate([base + yy * W + xx for yy in (y1, y2) for xx in (x1, x2)], axis=1)
-    return int(np.unique(elems // 8).size) * 32
+    g = granule_bytes // 4
+    return int(np.unique(elems // g).size) * granule_bytes
 
 
 def make_inputs(seed, n_sets, B, T=T_STATES, dof=2):
@@ -498,7 +500,8 @@ def main():
     checks['e2e_sdf_read_in_place'] = in_place_used
     e2e_val = e2e_run(lambda i: step_sdf(i, True))
     e2e_copy = e2e_run(lambda i: step_sdf(i, False))
-    sector_bytes = sum(tap_sector_bytes(h[0], h[3][:, 0]) for h in hsets) // len(hsets)
+    sector_bytes = sum(tap_sector_bytes(h[0], h[3][:, 0], 128) for h in hsets) // len(hsets)
+    sector_bytes_32 = sum(tap_sector_bytes(h[0], h[3][:, 0], 32) for h in hsets) // len(hsets)
     hs.step(hsets[0][0], hsets[0][1].reshape(B, d), hsets[0][2].reshape(B, d), hsets[0][3][:, 0])
     e2e_res = e2e_run(lambda i: hs.step(hsets[0][0], hsets[0][1].reshape(B, d), hsets[0][2].reshape(B, d), None, sdf_resident=True))
     # maps instead of SDFs across the bus: bit-packed occupancy in, exact EDT on the device (dgpmp2_gn_step_host_occ_f32)
@@ -734,11 +737,13 @@ def main():
                    'host': {'h2d_GBs_per_rank_all_ranks_copying': h2d_all, 'numa': numa, 'host_threads': host_threads()}},
         'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': hs.h2d_bytes + sector_bytes,
                 'd2h_bytes_per_step': hs.d2h_bytes, 'steps': Ke,
-                'h2d_breakdown': {'copied_trajectories_start_goal': hs.h2d_bytes, 'sdf_sectors_read_in_place_over_pcie': sector_bytes,
+                'h2d_breakdown': {'trajectories_start_goal': hs.h2d_bytes, 'sdf_128B_lines_read_in_place_over_pcie': sector_bytes,
+                                  'sdf_32B_sectors_touched_lower_bound': sector_bytes_32,
                                   'sdf_bytes_in_pinned_host_memory': hs.sdf_bytes},
-                'note': 'dgpmp2_gn_step_host_f32 with DGPMP2_SDF_IN_PLACE: inputs in pinned host memory every step; the '
-                        'trajectories are copied, the SDF is read where it lies (the kernel fetches the distinct 32-byte sectors '
-                        'its 4 taps per state touch, counted on the host from the same index arithmetic), results copied back'},
+                'note': 'dgpmp2_gn_step_host_f32 with DGPMP2_SDF_IN_PLACE: every operand in pinned host memory every step; the '
+                        'kernel reads the trajectories and the SDF where they lie (of the SDF only the distinct 128-byte lines its '
+                        '4 taps per state touch, counted on the host from the same index arithmetic) and writes the results '
+                        'back in place; config.e2e_copy_sdf is the same call with the whole SDF copied first'},
         'gpu_launches': K,
         'roofline': roofline,
         'roofline_k1': roofline_k1,
