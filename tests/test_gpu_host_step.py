@@ -81,6 +81,11 @@ def test_host_step_shared_sdf_stride_zero(dtype):
     ref = ops.gn_step(cp, th.cuda(), start.cuda(), goal.cuda(), sdf0.cuda().reshape(1, 1, *sdf0.shape))
     for a, b in zip(out, ref):
         assert torch.equal(a, b.cpu())
+    # ... and read in place from the pinned buffer (one shared field, every problem's taps over PCIe)
+    out_z = hs.step(th, start.reshape(B, d), goal.reshape(B, d), sdf0, in_place=True)
+    assert hs.last_sdf_read_in_place
+    for a, b in zip(out_z, ref):
+        assert torch.equal(a, b.cpu())
 
 
 def test_host_step_validates_its_arguments():
