@@ -1004,7 +1004,9 @@ sdf_lookup_kernel(const IO* __restrict__ sdf, int B, int H, int W, long long sdf
 // A pixel is background of one of the two transforms (distance 0 there), so each pixel needs ONE polarity: free pixels
 // look for the nearest obstacle, obstacle pixels for the nearest free pixel.  Bit-identical to the scipy path, including
 // scipy's behaviour for an image WITHOUT any background pixel (distance to a virtual pixel at row -1, column 0).
-// One CTA per image; 2 bytes + 2 mask bits of shared memory per pixel, so several images are resident per SM.
+// One CTA per image; 1 byte + 2 mask bits of shared memory per pixel and one stack byte per (task, row): 52 KB for a
+// 128 x 128 map, 4 images resident per SM (round 2, session 2: was 102 KB / 2 per SM; 0.355 -> 0.345 ms per 1024 maps -- the
+// kernel is bound by the divergent, serial envelope sweeps, not by occupancy).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int edt_nearest_bit(const unsigned* __restrict__ m, int NW, int x) {
   const int w = x >> 5, bp = x & 31;
@@ -1036,14 +1038,15 @@ struct OccBits { unsigned w; };
 struct EdtSmem {
   unsigned* m_obst;      // [Hp][NW] bit x of row y: pixel (y, x) is an obstacle
   unsigned* m_free;      // [Hp][NW] ... is free
-  unsigned char* g0;     // [Hp*Wp] distance along the row to the nearest OBSTACLE pixel (255: none in this row)
-  unsigned char* g1;     // [Hp*Wp] ... to the nearest FREE pixel
-  unsigned char* st_s;   // [Hp][threads] envelope stacks, entry k of the thread's task at [k * threads + tid]: parabola index (row)
-  unsigned char* st_t;   // [Hp][threads] ... first row at which that parabola is the lowest
+  unsigned char* g;      // [Hp*Wp] distance along the row to the nearest pixel of the OTHER polarity (255: none in this row);
+                         //         a pixel is at distance 0 from its own polarity, which the mask bit tells
+  unsigned char* st_s;   // [Hp][threads] envelope stacks, entry k of the thread's task at [k * threads + tid]: parabola index (row).
+                         //         The first row at which a parabola is the lowest is recomputed from its predecessor on a
+                         //         pop instead of being stored: half the stack bytes, 4 instead of 2 CTAs per SM.
   __host__ __device__ static size_t bytes(int Hp, int Wp, int threads) {
     const size_t NW = (size_t)(Wp + 31) / 32;
-    const size_t stacks = 2 * (size_t)Hp * threads, tmp = (size_t)Hp * Wp;      // (the stacks' area first holds one byte per pixel)
-    return 2 * (size_t)Hp * NW * 4 + 2 * (((size_t)Hp * Wp + 15) & ~(size_t)15) + (stacks > tmp ? stacks : tmp);
+    const size_t stacks = (size_t)Hp * threads, tmp = (size_t)Hp * Wp;      // (the stacks' area first holds one byte per pixel)
+    return 2 * (size_t)Hp * NW * 4 + (((size_t)Hp * Wp + 15) & ~(size_t)15) + (stacks > tmp ? stacks : tmp);
   }
 };
 
@@ -1056,8 +1059,8 @@ sdf_from_occupancy_kernel(const IN* __restrict__ im, int H, int W, int pad, doub
   EdtSmem S;
   S.m_obst = reinterpret_cast<unsigned*>(smem_raw);
   S.m_free = S.m_obst + (size_t)Hp * NW;
-  S.g0 = reinterpret_cast<unsigned char*>(S.m_free + (size_t)Hp * NW);
-  S.g1 = S.g0 + (((size_t)Hp * Wp + 15) & ~(size_t)15);
+  S.g = reinterpret_cast<unsigned char*>(S.m_free + (size_t)Hp * NW);
+  unsigned char* const after_g = S.g + (((size_t)Hp * Wp + 15) & ~(size_t)15);
   const IN* src = im + (size_t)blockIdx.x * H * W;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   // ---- A: row masks.  All pixels are fetched first (independent, coalesced loads; one DRAM latency for the image,
@@ -1075,7 +1078,7 @@ sdf_from_occupancy_kernel(const IN* __restrict__ im, int H, int W, int pad, doub
       any_free |= (bf != 0u);
     }
   } else {
-    unsigned char* tmp = S.g1 + (((size_t)Hp * Wp + 15) & ~(size_t)15);
+    unsigned char* tmp = after_g;
 #pragma unroll 8
     for (int i = threadIdx.x; i < Hp * Wp; i += blockDim.x) {
       const int y = i / Wp, x = i - y * Wp, yy = y - pad, xx = x - pad;
@@ -1107,14 +1110,11 @@ sdf_from_occupancy_kernel(const IN* __restrict__ im, int H, int W, int pad, doub
     const int y = i / Wp, x = i - y * Wp;
     // a pixel is at distance 0 from its own polarity: one search per pixel, for the other polarity
     const bool is_free = (S.m_free[y * NW + (x >> 5)] >> (x & 31)) & 1u;
-    const int d = edt_nearest_bit((is_free ? S.m_obst : S.m_free) + y * NW, NW, x);
-    S.g0[i] = (unsigned char)(is_free ? d : 0);
-    S.g1[i] = (unsigned char)(is_free ? 0 : d);
+    S.g[i] = (unsigned char)edt_nearest_bit((is_free ? S.m_obst : S.m_free) + y * NW, NW, x);
   }
   __syncthreads();
   // ---- C: lower envelope per (column, polarity) ----
-  S.st_s = S.g1 + (((size_t)Hp * Wp + 15) & ~(size_t)15);
-  S.st_t = S.st_s + (size_t)Hp * blockDim.x;
+  S.st_s = after_g;
   IO* dst = out + (size_t)blockIdx.x * Hp * Wp;
   const int NT = 2 * Wp;                                       // tasks: polarity * Wp + x
   constexpr int BIG = 1 << 20;                                 // "no pixel of that polarity in this row": above every real value
@@ -1122,35 +1122,54 @@ sdf_from_occupancy_kernel(const IN* __restrict__ im, int H, int W, int pad, doub
     const int j = base + threadIdx.x;
     const bool on = j < NT;
     const int pol = on ? j / Wp : 0, x = on ? j - pol * Wp : 0;
-    const unsigned char* g = (pol == 0 ? S.g0 : S.g1) + x;     // column x of that polarity's row distances
+    const unsigned char* g = S.g + x;                          // column x of the row distances
+    const unsigned* mf = S.m_free + (x >> 5);                  // ... and of the free-pixel mask
+    const int xb = x & 31;
     unsigned char* ss = S.st_s + threadIdx.x;                  // (the stacks are reused by every batch of tasks)
-    unsigned char* tt = S.st_t + threadIdx.x;
     const int SN = blockDim.x;
-    auto G = [&](int i) { const int a = g[(size_t)i * Wp]; return (a == 255) ? BIG : a * a; };
-    int q = 0, sq = 0, tq = 0, Gsq = 0;                        // top of the stack, cached in registers
+    // squared distance along row i from (i, x) to the nearest pixel of polarity `pol` (0: obstacle, 1: free): 0 for a
+    // pixel of that polarity itself
+    auto G = [&](int i) {
+      const int is_free = (int)((mf[(size_t)i * NW] >> xb) & 1u);
+      const int a = (is_free != pol) ? (int)g[(size_t)i * Wp] : 0;
+      return (a == 255) ? BIG : a * a;
+    };
+    // 1 + Sep(s, u) = first row at which parabola u (> s) is lower than parabola s:
+    // Sep(s, u) = floor((u^2 - s^2 + Gu - Gs) / (2 (u - s)))
+    auto first_row = [&](int s_, int Gs, int u_, int Gu) {
+      const int num = u_ * u_ - s_ * s_ + Gu - Gs, den = 2 * (u_ - s_);
+      int sep = (int)__fdividef((float)num, (float)den);
+      sep += ((sep + 1) * den <= num) ? 1 : 0;
+      sep -= (sep * den > num) ? 1 : 0;
+      return 1 + sep;
+    };
+    // top of the stack cached in registers: parabola sq, lowest from row tq on, Gsq = G(sq)
+    auto reload_top = [&](int q, int& sq, int& tq, int& Gsq) {
+      sq = ss[(size_t)q * SN];
+      Gsq = G(sq);
+      if (q == 0) { tq = 0; return; }
+      const int sp = ss[(size_t)(q - 1) * SN];
+      tq = first_row(sp, G(sp), sq, Gsq);
+    };
+    int q = 0, sq = 0, tq = 0, Gsq = 0;
     if (on) {
       Gsq = G(0);
-      ss[0] = 0; tt[0] = 0;
+      ss[0] = 0;
       for (int u = 1; u < Hp; ++u) {
         const int Gu = G(u);
         // pop parabolas that the one at u beats at the start of their interval
         while (q >= 0 && (tq - sq) * (tq - sq) + Gsq > (tq - u) * (tq - u) + Gu) {
           --q;
-          if (q >= 0) { sq = ss[(size_t)q * SN]; tq = tt[(size_t)q * SN]; Gsq = G(sq); }
+          if (q >= 0) reload_top(q, sq, tq, Gsq);
         }
         if (q < 0) {
           q = 0; sq = u; tq = 0; Gsq = Gu;
-          ss[0] = (unsigned char)u; tt[0] = 0;
+          ss[0] = (unsigned char)u;
         } else {
-          // Sep(sq, u) = floor((u^2 - sq^2 + Gu - Gsq) / (2 (u - sq))) >= tq >= 0: last row at which parabola sq is <= parabola u
-          const int num = u * u - sq * sq + Gu - Gsq, den = 2 * (u - sq);
-          int sep = (int)__fdividef((float)num, (float)den);
-          sep += ((sep + 1) * den <= num) ? 1 : 0;
-          sep -= (sep * den > num) ? 1 : 0;
-          const int w = 1 + sep;
+          const int w = first_row(sq, Gsq, u, Gu);             // >= tq >= 0
           if (w < Hp) {
             ++q; sq = u; tq = w; Gsq = Gu;
-            ss[(size_t)q * SN] = (unsigned char)u; tt[(size_t)q * SN] = (unsigned char)w;
+            ss[(size_t)q * SN] = (unsigned char)u;
           }
         }
       }
@@ -1159,7 +1178,7 @@ sdf_from_occupancy_kernel(const IN* __restrict__ im, int H, int W, int pad, doub
     for (int u = Hp - 1; u >= 0; --u) {
       if (on) {
         const int d2 = (u - sq) * (u - sq) + Gsq;
-        const bool is_free = S.g1[(size_t)u * Wp + x] == 0;
+        const bool is_free = ((mf[(size_t)u * NW] >> xb) & 1u) != 0u;
         if ((pol == 0) == is_free) {          // free pixels take the distance to the obstacles, obstacle pixels to free space
           // EDT(im) for free pixels (-> nearest obstacle), EDT(1 - im) for obstacle pixels (-> nearest free pixel).  No
           // background pixel at all (uniform): scipy (1.18) measures from a virtual pixel at row -1, column 0.
@@ -1170,7 +1189,7 @@ sdf_from_occupancy_kernel(const IN* __restrict__ im, int H, int W, int pad, doub
         }
         if (u == tq && q > 0) {
           --q;
-          sq = ss[(size_t)q * SN]; tq = tt[(size_t)q * SN]; Gsq = G(sq);
+          reload_top(q, sq, tq, Gsq);
         }
       }
     }
