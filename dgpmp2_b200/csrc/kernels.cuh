@@ -269,6 +269,39 @@ __device__ __forceinline__ void early_sdf_prefetch(const KParams& P, int T, int 
   }
 }
 
+// Staging of the CTA's trajectories fused with the early SDF prefetch: returns false (nothing done) when the global
+// trajectory is not aligned for the vector loads.  V = 16 bytes when a state is a multiple of 16 bytes, else 8.
+template <int D, typename IO>
+__device__ __forceinline__ bool stage_and_prefetch(const KParams& P, const StepSmem<D, IO>& S, int T, int NP, int np, int b0,
+                                                   const IO* __restrict__ th, const IO* __restrict__ sdf) {
+  constexpr int SB = D * (int)sizeof(IO);                       // bytes per state
+  using V = typename std::conditional<SB % 16 == 0, typename std::conditional<sizeof(IO) == 4, float4, double2>::type,
+                                      typename std::conditional<sizeof(IO) == 4, float2, double>::type>::type;
+  constexpr int NV = SB / (int)sizeof(V), EV = (int)(sizeof(V) / sizeof(IO));
+  if ((reinterpret_cast<unsigned long long>(th) & (sizeof(V) - 1)) != 0ull) return false;   // uniform
+  for (int p = threadIdx.x; p < NP; p += blockDim.x) S.fail[p] = 0;
+  const V* src = reinterpret_cast<const V*>(th + (size_t)b0 * T * D);
+  V* dst = reinterpret_cast<V*>(S.th);
+  const float inv_T = P.plan.inv_T;
+  for (int m = threadIdx.x; m < np * T; m += blockDim.x) {
+    V v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = __ldg(src + (size_t)m * NV + k);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) dst[(size_t)m * NV + k] = v[k];
+    const IO* e = reinterpret_cast<const IO*>(&v[0]);           // x, y are the first two elements of the state
+    static_assert(EV >= 2, "a vector holds at least x and y");
+    const float x = (float)e[0], y = (float)e[1];
+    const int p = fast_div(m, inv_T);
+    const float fx = (float)P.orig_x + x * (float)P.inv_res, fy = (float)P.orig_y - y * (float)P.inv_res;
+    const int ix = min(max(__float2int_rd(fx), 0), P.W - 1), iy = min(max(__float2int_rd(fy), 0), P.H - 1);
+    const IO* q = sdf + (size_t)(b0 + p) * P.sdf_sb + (size_t)iy * P.W + ix;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q + ((iy + 1 < P.H) ? P.W : 0)));
+  }
+  return true;
+}
+
 // One fused Gauss-Newton iteration.  grid = ceil(B / NP), block = NP * TPP threads (rounded to a warp).
 template <int DOF, typename IO>
 __global__ void __launch_bounds__(DOF == 2 ? 512 : 256)
@@ -294,8 +327,14 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
   DGPMP2_STAMP(0);
 
   const bool early = (P.prefetch & 2) != 0;
-  if (early) early_sdf_prefetch<D, IO>(P, T, b0, np, th, sdf);
-  cta_prologue<D, IO>(P, S, T, NP, np, th + (size_t)b0 * T * D, false);
+  // One pass (when the trajectory is vector-aligned): every thread loads whole states in natural order, stages them and
+  // requests the SDF rows of their obstacle factors -- one global round trip instead of the prefetch pass followed by the
+  // staging pass (measured, B=1024, T=64: 16.59 -> 16.17 us L2-warm, 17.96 -> 17.84 us DRAM-cold; same bits).
+  if (early && stage_and_prefetch<D, IO>(P, S, T, NP, np, b0, th, sdf)) {
+  } else {
+    if (early) early_sdf_prefetch<D, IO>(P, T, b0, np, th, sdf);
+    cta_prologue<D, IO>(P, S, T, NP, np, th + (size_t)b0 * T * D, false);
+  }
   __syncthreads();
   DGPMP2_STAMP(1);
 
@@ -536,8 +575,11 @@ gn_step_bwd_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict_
   const int np = min(NP, P.B - b0);
 
   const bool early = (P.prefetch & 2) != 0;
-  if (early) early_sdf_prefetch<D, IO>(P, T, b0, np, th, sdf);
-  cta_prologue<D, IO>(P, S, T, NP, np, th + (size_t)b0 * T * D, false);
+  if (early && stage_and_prefetch<D, IO>(P, S, T, NP, np, b0, th, sdf)) {
+  } else {
+    if (early) early_sdf_prefetch<D, IO>(P, T, b0, np, th, sdf);
+    cta_prologue<D, IO>(P, S, T, NP, np, th + (size_t)b0 * T * D, false);
+  }
   {
     const IO* src = dth + (size_t)b0 * T * D;
     const int n = np * T * D;
