@@ -617,9 +617,13 @@ __device__ __forceinline__ void bcr_tail(double* __restrict__ nodes, int T, int 
 // level1_eliminated (uniform): the records of the level-1 nodes already hold L, E, F, g (skip that phase).
 // On exit every record's [oR, oR+D) holds x_t.  fail[p] (shared, pre-zeroed) receives t+1 of a node
 // of problem p whose pivot was not positive.  Must be called by ALL threads of the CTA (barriers).
-template <int D>
+// side_work(first_idle_warp) is called by every thread between the sequential tail and its barrier: the tail keeps only
+// the first ceil(kLPN * np / 32) warps busy, so the caller can give the others something that does not depend on the
+// solve (gn_step_kernel: the per-problem error reductions).
+struct BcrNoSideWork { __device__ __forceinline__ void operator()(int) const {} };
+template <int D, typename SideWork = BcrNoSideWork>
 __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const BcrPlan& plan, int T, int np, int* fail,
-                                          bool level1_eliminated = false) {
+                                          bool level1_eliminated = false, SideWork side_work = SideWork()) {
   const int nl = plan.nl, wide_min = plan.wide_min;
 
   // ------------------------------ forward elimination ------------------------------
@@ -646,6 +650,7 @@ __device__ __forceinline__ void bcr_solve(double* __restrict__ nodes, const BcrP
 
   // ------------------------------ remaining chain (root when tail_max == 1) ------------------------------
   bcr_tail<D>(nodes, T, np, plan.tail_stride, plan.tail_nc, fail);
+  side_work((kLPN * np + 31) >> 5);
   __syncthreads();
   DGPMP2_BCR_STAMP(5);
 

@@ -161,9 +161,12 @@ __device__ __forceinline__ void reduce_per_problem(const double* base, int strid
 
 // Same for two interleaved quantities stored as adjacent doubles (16-byte aligned): `base[p * pstride + i * stride + {0, 1}]`.
 // Each component is summed in exactly the order reduce_per_problem uses.  `f(p, sum0, sum1)` is called by lane 0.
+// wbase: the reductions are done by the warps [wbase, nwarps) only (warp wbase + k takes problems k, k + nwarps - wbase, ...)
 template <typename F>
-__device__ __forceinline__ void reduce2_per_problem(const double* base, int stride, size_t pstride, int np, int T, F f) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+__device__ __forceinline__ void reduce2_per_problem(const double* base, int stride, size_t pstride, int np, int T, F f,
+                                                    int wbase = 0) {
+  const int warp = (threadIdx.x >> 5) - wbase, lane = threadIdx.x & 31, nwarps = (blockDim.x >> 5) - wbase;
+  if (warp < 0) return;
   for (int p = warp; p < np; p += nwarps) {
     double s0 = 0.0, s1 = 0.0;
     for (int i = lane; i < T; i += 32) {
@@ -221,11 +224,24 @@ __device__ void g_phase_clock_fwd(int i) { g_phase_clock[i] = clock64(); }
 #define DGPMP2_STAMP(i) do { } while (0)
 #endif
 
+// err / err_ext of the CTA's problems: one deterministic warp reduction per problem over the states' partials (which the
+// solver never touches), done by the warps [wbase, nwarps)
+template <int DOF, typename IO>
+__device__ __forceinline__ void step_errors(const KParams& P, const StepSmem<2 * DOF, IO>& S, int T, int b0, int np,
+                                            IO* __restrict__ err, IO* __restrict__ err_ext, int wbase) {
+  using N = Node<2 * DOF>;
+  const double invM = 1.0 / (double)P.M;
+  reduce2_per_problem(S.nodes + N::oX, N::kStride, N::problem_stride(T), np, T, [&](int p, double s0, double s1) {
+    err[b0 + p] = (IO)(s0 * invM);
+    err_ext[b0 + p] = (IO)(s1 * invM);
+  }, wbase);
+}
+
 // dth (natural order -> coalesced stores), err / err_ext (one deterministic warp reduction per problem), status
 template <int DOF, typename IO>
 __device__ __forceinline__ void step_epilogue(const KParams& P, const StepSmem<2 * DOF, IO>& S, int T, int b0, int np,
                                               IO* __restrict__ dth, IO* __restrict__ err, IO* __restrict__ err_ext,
-                                              int* __restrict__ status) {
+                                              int* __restrict__ status, bool errors_done = false) {
   constexpr int D = 2 * DOF;
   using N = Node<D>;
   {
@@ -240,11 +256,7 @@ __device__ __forceinline__ void step_epilogue(const KParams& P, const StepSmem<2
       store_state<D, IO>(dst + (size_t)i * D, x, vec);
     }
   }
-  const double invM = 1.0 / (double)P.M;
-  reduce2_per_problem(S.nodes + N::oX, N::kStride, N::problem_stride(T), np, T, [&](int p, double s0, double s1) {
-    err[b0 + p] = (IO)(s0 * invM);
-    err_ext[b0 + p] = (IO)(s1 * invM);
-  });
+  if (!errors_done) step_errors<DOF, IO>(P, S, T, b0, np, err, err_ext, 0);
   if (status != nullptr)
     for (int p = threadIdx.x; p < np; p += blockDim.x) status[b0 + p] = S.fail[p];
 }
@@ -343,10 +355,14 @@ gn_step_kernel(const KParams P, const KWeights<IO> Wt, const IO* __restrict__ th
   __syncthreads();
   DGPMP2_STAMP(2);
 
-  bcr_solve<D>(S.nodes, P.plan, T, np, S.fail, fuse1);   // ends with a barrier
+  // the error reductions ride in the warps the sequential tail leaves idle (when there are any)
+  const bool side = ((kLPN * np + 31) >> 5) < (int)(blockDim.x >> 5);
+  bcr_solve<D>(S.nodes, P.plan, T, np, S.fail, fuse1, [&](int first_idle_warp) {
+    if (side) step_errors<DOF, IO>(P, S, T, b0, np, err, err_ext, first_idle_warp);
+  });   // ends with a barrier
   DGPMP2_STAMP(3);
 
-  step_epilogue<DOF, IO>(P, S, T, b0, np, dth, err, err_ext, status);
+  step_epilogue<DOF, IO>(P, S, T, b0, np, dth, err, err_ext, status, side);
   DGPMP2_STAMP(4);
 }
 
